@@ -1,0 +1,252 @@
+/*
+ * nqcuda.h -- C ABI of libnqcuda, the B200 (sm_100a) implementation of NeuralQuantum.jl's
+ * variational-Monte-Carlo hot path.
+ *
+ * Every entry point replaces one interface of the reference (cited "ref:" with file:line relative
+ * to the NeuralQuantum.jl v0.2.0 checkout) and is what a Julia `ccall` shim binds.
+ *
+ * Conventions
+ *   - All functions return an int status: NQ_OK (0) or a negative NQ_ERR_* code.  No exception or
+ *     exit crosses the boundary; nq_last_error(ctx) returns the message of the last failure.
+ *   - Arrays are dense, COLUMN-MAJOR and 0-offset exactly as Julia lays them out:
+ *       states sigma [N, B]   (site fastest), values -1/+1 (HomogeneousSpin) or 0/1 (HomogeneousFock)
+ *       log psi      [B]
+ *       O = grad     [P, B]   (parameter fastest; leading dimension ldO >= P), functor order:
+ *                     RBM a,b,W | RBMSplit ar,ac,b,Wr,Wc | NDM b_mu,h_mu,w_mu,u_mu,b_lam,h_lam,d_lam,w_lam,u_lam
+ *                     with matrices W[M,N] flattened column-major (k + M*j)
+ *       S            [P, P]
+ *     Complex numbers are interleaved (re, im).
+ *   - Every data pointer may be a HOST pointer or a DEVICE pointer (detected with
+ *     cudaPointerGetAttributes).  Host buffers are staged through device scratch inside the call
+ *     and the call returns after the results are back on the host.  With device pointers the call
+ *     only enqueues work on the context's stream.
+ *   - Caller owns all buffers it passes; the library never keeps a caller pointer after return.
+ *     Device state (parameters, tables, chains, workspaces) lives behind opaque handles.
+ *   - Handles are not thread-safe; distinct contexts may be used from distinct threads.
+ *   - There is NO CPU fallback: without a CUDA device nq_ctx_create fails with NQ_ERR_CUDA.
+ */
+#ifndef NQCUDA_H
+#define NQCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NQ_VERSION 100
+
+/* ---- status codes (ref: Julia exceptions; SRDirect.jl:79 PosDefException; SRIterative.jl:133-150) */
+enum {
+    NQ_OK = 0,
+    NQ_ERR_ARG = -1,            /* bad argument / null handle                      */
+    NQ_ERR_SHAPE = -2,          /* inconsistent sizes                              */
+    NQ_ERR_CUDA = -3,           /* CUDA runtime failure (message in nq_last_error) */
+    NQ_ERR_NCCL = -4,           /* NCCL failure or communicator not initialised    */
+    NQ_ERR_NOT_POSDEF = -5,     /* Cholesky met a non-positive pivot (info = index)*/
+    NQ_ERR_NOT_CONVERGED = -6,  /* CG hit maxiter; dw is still returned            */
+    NQ_ERR_UNSUPPORTED = -7,    /* valid request outside the built path            */
+    NQ_ERR_ALLOC = -8
+};
+
+/* ---- enumerations */
+typedef enum { NQ_RBM = 0, NQ_RBMSPLIT = 1, NQ_NDM = 2 } nq_machine_kind;
+typedef enum { NQ_SOFTPLUS = 0, NQ_LOGCOSH = 1 } nq_activation;          /* ref: Networks/activation.jl:5-29 */
+typedef enum { NQ_F32 = 0, NQ_F64 = 1, NQ_C64 = 2, NQ_C128 = 3 } nq_dtype;
+typedef enum { NQ_SPIN = 0, NQ_FOCK = 1 } nq_hilbert;                    /* values -1/+1 | 0/1, local dim 2 */
+typedef enum { NQ_KET = 0, NQ_SUPER = 1 } nq_space;                      /* H on sigma | Liouvillian on (sigma,sigma') */
+typedef enum { NQ_SOLVE_CHOLESKY = 0, NQ_SOLVE_CG = 1 } nq_solver;       /* ref: SR/SR.jl sr_cholesky | sr_cg */
+
+typedef struct nq_ctx_s* nq_ctx_t;
+typedef struct nq_machine_s* nq_machine_t;
+typedef struct nq_operator_s* nq_operator_t;
+typedef struct nq_sampler_s* nq_sampler_t;
+
+/* ======================================================================================
+ * Context.  One context = one device + one stream.  ref: one sampler object per task/rank
+ * (Parallel/Threads/threads_wrappers.jl:14-31, Parallel/MPI/mpi.jl).
+ * `stream` is a cudaStream_t (NULL: the library creates its own non-blocking stream).
+ * ==================================================================================== */
+int nq_version(void);
+const char* nq_status_string(int status);
+int nq_ctx_create(int device, void* stream, nq_ctx_t* out);
+int nq_ctx_destroy(nq_ctx_t ctx);
+const char* nq_last_error(nq_ctx_t ctx);
+int nq_ctx_sync(nq_ctx_t ctx);
+/* number of kernels this library launched on the context so far (bench.py "gpu_launches") */
+int nq_ctx_launch_count(nq_ctx_t ctx, uint64_t* out);
+/* `info` of the last NQ_ERR_NOT_POSDEF (failing pivot, 0-based) */
+int nq_ctx_last_info(nq_ctx_t ctx, int64_t* out);
+
+/* ======================================================================================
+ * Configurations: reference float arrays <-> bit-packed device words.
+ * Packed layout: uint64 words[B][W64], W64 = ceil(N/64); bit (j%64) of word j/64 = local digit of
+ * site j (0-based): digit = (v+1)/2 for NQ_SPIN, v for NQ_FOCK.
+ * ref: States/States.jl:12-32 (dense [N,B,L] float arrays), Hilbert/HomogeneousSpin.jl:156-179.
+ * `sdtype` is the element type of the float arrays (NQ_F32 or NQ_F64).
+ * ==================================================================================== */
+int nq_states_words(int N);
+int nq_pack_states(nq_ctx_t ctx, nq_hilbert h, int N, int64_t B, const void* sigma, nq_dtype sdtype,
+                   uint64_t* packed);
+int nq_unpack_states(nq_ctx_t ctx, nq_hilbert h, int N, int64_t B, const uint64_t* packed,
+                     void* sigma, nq_dtype sdtype);
+
+/* ======================================================================================
+ * Machines.  ref: machine plugin interface, base_batched_networks.jl:20-104
+ *   cache(net,batch_sz) / logpsi!(out,net,cache,sigma...) / logpsi_and_grad!(grad,out,net,cache,sigma...)
+ * RBM:      Networks/ClosedSystems/RBM.jl:50-51, RBMBatched.jl:37-91
+ * RBMSplit: Networks/MixedDensityMatrix/RBMSplit.jl:49-50, RBMSplitBatched.jl:35-101
+ * NDM:      Networks/MixedDensityMatrix/NDM.jl:76-96, NDMBatched.jl:94-280
+ * dtype = parameter type: NQ_F32/NQ_F64 (real weights) or NQ_C64/NQ_C128 (complex weights);
+ * NDM takes real parameters only and outputs complex.  out_type: RBM/RBMSplit = dtype, NDM = complex.
+ * M = hidden units, A = ancillas (NDM only, else 0).  RBMSplit ignores `act` (softplus hard-wired).
+ * ==================================================================================== */
+int nq_machine_create(nq_ctx_t ctx, nq_machine_kind kind, nq_hilbert h, int N, int M, int A,
+                      nq_activation act, nq_dtype dtype, nq_machine_t* out);
+int nq_machine_destroy(nq_machine_t m);
+int nq_machine_nparams(nq_machine_t m, int64_t* P);
+int nq_machine_out_dtype(nq_machine_t m, nq_dtype* out);   /* ref: out_type(net) */
+/* flat parameter vector in functor order, P elements of the machine dtype. ref: functor.jl:41, utils/loading.jl:8-14 */
+int nq_machine_set_params(nq_machine_t m, const void* params, int64_t P);
+int nq_machine_get_params(nq_machine_t m, void* params, int64_t P);
+
+/* logpsi!(out, net, cache, sigma[, sigma'])  -- `scol` must be NULL for RBM. out: [B] of out_type */
+int nq_logpsi(nq_machine_t m, const void* srow, const void* scol, nq_dtype sdtype, int64_t B, void* out);
+/* log_prob_psi!: 2*Re(log psi).  ref: base_batched_networks.jl:255-259.  out: [B] real */
+int nq_log_prob(nq_machine_t m, const void* srow, const void* scol, nq_dtype sdtype, int64_t B, void* out);
+/* logpsi_and_grad!: out [B], O [P,B] with leading dimension ldO (elements of out_type) */
+int nq_logpsi_grad(nq_machine_t m, const void* srow, const void* scol, nq_dtype sdtype, int64_t B,
+                   void* out, void* O, int64_t ldO);
+/* same on bit-packed configurations already on the device (no conversion pass) */
+int nq_logpsi_packed(nq_machine_t m, const uint64_t* prow, const uint64_t* pcol, int64_t B, void* out);
+int nq_logpsi_grad_packed(nq_machine_t m, const uint64_t* prow, const uint64_t* pcol, int64_t B,
+                          void* out, void* O, int64_t ldO);
+
+/* ======================================================================================
+ * Operators: per-local-row connection tables.
+ * ref: Operators/Operators/KLocalOperator.jl:54-112 (tables), :183-199 (enumeration),
+ *      KLocalOperatorSum.jl:65-72, KLocalOperatorTensor.jl:129-157, KLocalLiouvillian.jl:46-52.
+ * A "part" is one KLocalOperator: k sites (0-based, local digit i <-> part_sites[i]) and 2^k rows;
+ * row r holds entries [row_ptr[r], row_ptr[r+1]) = (mel, local flip mask: bit i set <=> site i changes).
+ * Rows of all parts are concatenated in part order (row_ptr has sum_p 2^k_p + 1 entries).  Entry 0 of
+ * every row is the diagonal one (flip mask 0).
+ * A "term" is visited in order and references a left part (acts on sigma; row index from sigma) and/or a
+ * right part (acts on sigma'), -1 for identity; with both, entries are enumerated left-major and
+ * mel = mel_l*mel_r (KLocalOperatorTensor.jl:146-154).  For NQ_KET only term_left is used.
+ * ==================================================================================== */
+int nq_operator_create(nq_ctx_t ctx, nq_space space, int N,
+                       int n_parts, const int32_t* part_nsites, const int32_t* part_sites,
+                       const int64_t* row_ptr, const double* entry_mel /* complex128 */,
+                       const uint32_t* entry_flip,
+                       int n_terms, const int32_t* term_left, const int32_t* term_right,
+                       nq_operator_t* out);
+int nq_operator_destroy(nq_operator_t op);
+/* upper bound on the number of connections of one configuration */
+int nq_operator_max_connections(nq_operator_t op, int64_t* out);
+/* row_valdiff! over a batch (integer-parity path): for sample b, counts[b] connections in reference
+ * order, zero matrix elements included; mels [max_conn,B] complex128; flips_row/flips_col
+ * [W64, max_conn, B] uint64 global flip masks (flips_col may be NULL for NQ_KET).
+ * ref: Operators/BaseOperators.jl:25-36, KLocalOperator.jl:151-159 */
+int nq_connections(nq_operator_t op, nq_hilbert h, const void* srow, const void* scol, nq_dtype sdtype,
+                   int64_t B, int64_t max_conn, int32_t* counts, double* mels,
+                   uint64_t* flips_row, uint64_t* flips_col);
+
+/* E_loc(sigma) = sum_c mel_c psi(eta_c)/psi(sigma).  out_loc [B] complex (C64 if machine is 32-bit, else C128).
+ * logpsi may be NULL (recomputed).  Works for NQ_KET on RBM and for NQ_SUPER on RBMSplit/NDM.
+ * ref: Accumulators/AccumulatorObsScalar.jl:52-137, AccumulatorLogPsi.jl:56-126, BatchedValSampler.jl:70-95 */
+int nq_local_scalar(nq_machine_t m, nq_operator_t op, const void* srow, const void* scol, nq_dtype sdtype,
+                    int64_t B, const void* logpsi, void* out_loc);
+/* L_loc and grad L_loc = sum_c mel_c r_c grad log rho(eta_c) over ALL non-zero connections.
+ * out_gloc [P,B] complex, leading dimension ld; may be NULL (value only).
+ * ref: Accumulators/AccumulatorObsGrad.jl:39-127, AccumulatorLogGradPsi.jl:57-120, BatchedGradSampler.jl:87-97 */
+int nq_local_grad(nq_machine_t m, nq_operator_t op, const void* srow, const void* scol, nq_dtype sdtype,
+                  int64_t B, const void* logpsi, void* out_loc, void* out_gloc, int64_t ld);
+int nq_local_scalar_packed(nq_machine_t m, nq_operator_t op, const uint64_t* prow, const uint64_t* pcol,
+                           int64_t B, void* out_loc);
+int nq_local_grad_packed(nq_machine_t m, nq_operator_t op, const uint64_t* prow, const uint64_t* pcol,
+                         int64_t B, void* out_loc, void* out_gloc, int64_t ld);
+
+/* ======================================================================================
+ * Metropolis-Hastings sampler, LocalRule (single-site flip).
+ * ref: Samplers/Metropolis.jl:4-40 (ctor), :101-115 (init_sampler!), :124-167 (samplenext!),
+ *      Samplers/MCMCRules/LocalRule.jl:19-28, Hilbert/DoubledHilbert.jl:19-27.
+ * B chains; one stored sample = `passes` proposals (even `passes` is bumped to odd like the reference).
+ * Production mode draws (site, uniform) from Philox4x32-10 keyed by (seed, global chain id =
+ * chain_offset + chain), so results do not depend on how chains are sharded over GPUs.
+ * ==================================================================================== */
+int nq_sampler_create(nq_machine_t m, int64_t B, int passes, uint64_t seed, int64_t chain_offset,
+                      nq_sampler_t* out);
+int nq_sampler_destroy(nq_sampler_t s);
+int nq_sampler_set_state(nq_sampler_t s, const void* srow, const void* scol, nq_dtype sdtype);
+int nq_sampler_get_state(nq_sampler_t s, void* srow, void* scol, nq_dtype sdtype);
+/* rand!(rng, sigma, hilb): uniformly random configurations (Metropolis.jl:106) */
+int nq_sampler_randomize(nq_sampler_t s);
+/* one samplenext! with supplied randomness: sites [passes,B] int32 1-based in 1..N (1..2N doubled),
+ * uniforms [passes,B] of the machine's real type; accept_out [passes,B] uint8 (1 = accepted), may be NULL */
+int nq_sampler_replay(nq_sampler_t s, const int32_t* sites, const void* uniforms, uint8_t* accept_out);
+/* `burn` discarded + `L` stored samples per chain.  Outputs (each may be NULL):
+ * packed [L][B][W64] device/host words, or float arrays [N,B,L] of sdtype. */
+int nq_sampler_sample(nq_sampler_t s, int burn, int L, uint64_t* prow, uint64_t* pcol,
+                      void* srow, void* scol, nq_dtype sdtype);
+int nq_sampler_counters(nq_sampler_t s, int64_t* passes_done, int64_t* passes_accepted);
+
+/* ======================================================================================
+ * Stochastic reconfiguration.
+ * dtype below = element type of O (NQ_F32/F64 for real-weight RBM/RBMSplit; NQ_C64/C128 otherwise).
+ * ==================================================================================== */
+/* <O> and O <- O - <O> in place.  ref: BaseIterativeSampler.jl:19-26.  avg [P] */
+int nq_center(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype, void* avg);
+/* gradC = E_loc * Oc' / Ns  (F_k = <E_loc conj(Oc_k)>).  ref: BatchedValSampler.jl:97-115.
+ * Eloc [Ns] complex of matching precision; gradC [P] complex */
+int nq_force_ket(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype,
+                 const void* Eloc, void* gradC);
+/* gradC = conj(L_loc * gradL' / Ns - <|L_loc|^2> avg').  ref: BatchedGradSampler.jl:99-118.
+ * Returns the cost <|L_loc|^2> in *cost (host double). */
+int nq_force_liouvillian(nq_ctx_t ctx, const void* Lloc, const void* gLloc, int64_t ld, int64_t P,
+                         int64_t Ns, nq_dtype dtype, const void* avg, void* gradC, double* cost);
+/* S and F from the centred O.  real_params != 0: S = Re(Oc Oc^H)/Ns (real [P,P]), F = Re(gradC);
+ * else S = conj(Oc Oc^H)/Ns (complex), F = gradC.  Ns_total = global sample count used to
+ * normalise (== Ns on one GPU; under sharding the partial S is all-reduced by the caller, quirk Q5).
+ * ref: SR/SRDirect.jl:26-49, SRIterative.jl:45-62 */
+int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total,
+                nq_dtype dtype, const void* gradC, int real_params, void* S, void* F);
+/* (S + eps I) dw = F.  sdtype = element type of S/F/dw (real or complex).  S is overwritten.
+ * CHOLESKY: NQ_ERR_NOT_POSDEF if a pivot <= 0.  CG: IterativeSolvers-0.8.1 semantics, x0 = 0,
+ * stop ||r|| <= tol ||F||, maxiter (<=0: 10 P); NQ_ERR_NOT_CONVERGED when exhausted.
+ * ref: SRDirect.jl:51-90, SRIterative.jl:71-153 */
+int nq_sr_solve(nq_ctx_t ctx, void* S, const void* F, int64_t P, nq_dtype sdtype, double eps,
+                nq_solver algo, double tol, int64_t maxiter, void* dw, int64_t* iters);
+/* matrix-free CG: v -> eps v + conj(Oc)(conj(Oc)^H v)/Ns_total (complex nets) or
+ * (Or Or^T + Oi Oi^T) v/Ns_total (real_params).  With a communicator the partial products are
+ * all-reduced every iteration.  ref: SR/SR_notfull.jl:47-148, SRIterative.jl:117-132 */
+int nq_sr_solve_matfree(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total,
+                        nq_dtype dtype, const void* F, int real_params, double eps, double tol,
+                        int64_t maxiter, void* dw, int64_t* iters);
+/* w <- w - eta dw on the machine's device parameters.  dw has the machine dtype (real for NDM).
+ * ref: Optimisers/rules.jl:11-17, apply.jl:25-73 */
+int nq_update(nq_machine_t m, const void* dw, double eta);
+/* stat_analysis over [B chains, L] values (column-major [B,L]); out = {mean_re, mean_im, error,
+ * variance, tau, R} host doubles.  vdtype: NQ_F32/F64/C64/C128.  ref: utils/stats.jl:26-50 */
+int nq_stat_analysis(nq_ctx_t ctx, const void* vals, int64_t B, int64_t L, nq_dtype vdtype, double out[6]);
+
+/* out[i] = |vals[i]|^2 (real of the same precision).  ref: BatchedGradSampler.jl:99 (abs2.(local_vals)) */
+int nq_abs2(nq_ctx_t ctx, const void* vals, int64_t n, nq_dtype vdtype, void* out);
+
+/* ======================================================================================
+ * Parallel backend: chains are sharded over ranks (one GPU each); partial sums are reduced with
+ * NCCL all-reduce over NVLink.  ref: Parallel/not_parallel.jl:1-19, Parallel/MPI/mpi.jl:21-74
+ * (workers_sum!, workers_mean!, num_workers, worker_local_seed).
+ * ==================================================================================== */
+#define NQ_UNIQUE_ID_BYTES 128
+int nq_comm_unique_id(uint8_t id[NQ_UNIQUE_ID_BYTES]);
+int nq_comm_init(nq_ctx_t ctx, int nranks, int rank, const uint8_t id[NQ_UNIQUE_ID_BYTES]);
+int nq_comm_destroy(nq_ctx_t ctx);
+int nq_comm_size(nq_ctx_t ctx, int* nranks, int* rank);   /* 1, 0 without a communicator */
+int nq_allreduce_sum(nq_ctx_t ctx, void* buf, int64_t n, nq_dtype dtype);   /* device buffer, in place */
+int nq_allreduce_mean(nq_ctx_t ctx, void* buf, int64_t n, nq_dtype dtype);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NQCUDA_H */

@@ -1,0 +1,52 @@
+// nq_internal.cuh -- handle layouts and cross-file internal entry points of libnqcuda.
+#pragma once
+#include "nq_common.cuh"
+
+// scratch slot ids (one live buffer per slot per call)
+enum {
+    SL_IN0 = 0, SL_IN1, SL_IN2, SL_IN3, SL_IN4,
+    SL_OUT0, SL_OUT1, SL_OUT2, SL_OUT3,
+    SL_PROW, SL_PCOL, SL_LOGPSI, SL_W0, SL_W1, SL_W2, SL_W3, SL_W4, SL_W5
+};
+
+struct nq_machine_s {
+    nq_ctx_t ctx;
+    nq_machine_kind kind;
+    nq_hilbert hilb;
+    int N, M, A;
+    nq_activation act;
+    nq_dtype dtype;       // parameter dtype
+    nq_dtype out_dtype;   // log psi / gradient dtype
+    int64_t P;
+    void* params;         // device, P elements of dtype
+    bool doubled() const { return kind != NQ_RBM; }
+};
+
+struct nq_operator_s {
+    nq_ctx_t ctx;
+    nq_space space;
+    int N;
+    int n_parts, n_terms;
+    int64_t n_rows, n_entries;
+    int64_t max_conn;
+    int max_part_sites;
+    // device tables
+    int32_t* part_nsites;   // [n_parts]
+    int32_t* part_site_ptr; // [n_parts+1] offsets into part_sites
+    int32_t* part_sites;    // 0-based
+    int64_t* part_row0;     // [n_parts] first row of the part in row_ptr
+    int64_t* row_ptr;       // [n_rows+1]
+    double* entry_mel;      // complex128 interleaved [n_entries]
+    uint32_t* entry_flip;   // [n_entries]
+    int32_t* term_left;     // [n_terms]
+    int32_t* term_right;    // [n_terms]
+};
+
+// device-pointer internals shared between translation units
+int nq_pack_device(nq_ctx_t ctx, nq_hilbert h, int N, int64_t B, const void* dsigma, nq_dtype sdtype, uint64_t* dpacked);
+int nq_unpack_device(nq_ctx_t ctx, nq_hilbert h, int N, int64_t B, const uint64_t* dpacked, void* dsigma, nq_dtype sdtype);
+int nq_machine_eval_device(nq_machine_t m, const uint64_t* prow, const uint64_t* pcol, int64_t B,
+                           void* out, void* O, int64_t ldO);
+struct NqStage;
+int nq_stage_pack(nq_machine_t m, NqStage& st, const void* srow, const void* scol, nq_dtype sdtype, int64_t B,
+                  const uint64_t** prow, const uint64_t** pcol);

@@ -1,0 +1,501 @@
+// nq_sampler.cu -- K4: Metropolis-Hastings local-flip sampler, one Markov chain per warp.
+//
+// The reference re-evaluates the whole machine for every proposal (Samplers/Metropolis.jl:141-146,
+// O(M N) per pass) and loops serially over chains to propose (MCMCRules/LocalRule.jl:19-28).  Here a
+// warp owns a chain for the whole burn-in + sampling run inside ONE launch: the pre-activations
+// theta live in shared memory, a single flip changes theta by +-column of W (O(M) per pass), the
+// lanes own hidden units, the log-probability ratio is a warp-shuffle reduction and randomness is
+// Philox4x32-10 keyed by (seed, global chain id) so the chains do not depend on the GPU count.
+// Replay mode takes the proposal sites and uniforms from the caller instead: accept/reject
+// decisions are then comparable bit for bit with the oracle.
+//
+// Accept rule (Metropolis.jl:148-154): accept iff  u - exp(logp' - logp) < 0,  logp = 2 Re log psi,
+// evaluated in the machine's real precision.
+#include "nq_internal.cuh"
+
+struct nq_sampler_s {
+    nq_machine_t m;
+    int64_t B;
+    int passes;
+    uint64_t seed;
+    int64_t chain_offset;
+    uint64_t pass_base;       // proposals already drawn per chain (Philox counter)
+    uint64_t* prow;           // device [B][W64]
+    uint64_t* pcol;
+    unsigned long long* accepted;   // device counter
+    int64_t passes_done;
+};
+
+namespace {
+
+constexpr int MAXW = 4;   // N <= 256
+
+struct Philox {
+    uint32_t k0, k1;
+    __device__ __forceinline__ void round(uint32_t (&c)[4], uint32_t ka, uint32_t kb) {
+        const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+        uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+        uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ ka, n1 = lo1, n2 = hi0 ^ c[3] ^ kb, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    __device__ __forceinline__ void gen(uint32_t (&c)[4]) {
+        uint32_t ka = k0, kb = k1;
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            round(c, ka, kb);
+            ka += 0x9E3779B9u; kb += 0xBB67AE85u;
+        }
+    }
+};
+
+template <typename T> __device__ __forceinline__ T uniform01(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ float uniform01<float>(uint32_t a, uint32_t) { return (float)(a >> 8) * 5.9604644775390625e-8f; }
+template <> __device__ __forceinline__ double uniform01<double>(uint32_t a, uint32_t b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void randomize_kernel(uint64_t* __restrict__ prow, uint64_t* __restrict__ pcol, int64_t B, int N, int W64,
+                                 uint64_t seed, int64_t chain_offset, uint64_t epoch) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= B * W64) return;
+    int64_t b = i / W64;
+    int w = (int)(i % W64);
+    uint64_t gid = (uint64_t)(chain_offset + b);
+    Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)(epoch * 8 + w), 0x52414e44u /* "RAND" domain */};
+    ph.gen(c);
+    int nbits = N - 64 * w; nbits = nbits > 64 ? 64 : nbits;
+    uint64_t mask = nbits == 64 ? ~0ull : ((1ull << nbits) - 1);
+    prow[i] = (((uint64_t)c[1] << 32) | c[0]) & mask;
+    if (pcol) pcol[i] = (((uint64_t)c[3] << 32) | c[2]) & mask;
+}
+
+// shared memory per warp: items * (theta, f, theta_tentative, f_tentative)
+struct RunArgs {
+    int64_t B;
+    int N, M, A, hilb, passes, burn, L, replay;
+    uint64_t seed, pass_base;
+    int64_t chain_offset;
+    const int32_t* sites;      // replay: [passes][B], 1-based
+    const void* uniforms;      // replay: [passes][B]
+    uint8_t* accept_out;       // replay: [passes][B]
+    uint64_t* out_prow;        // [L][B][W64]
+    uint64_t* out_pcol;
+    unsigned long long* accepted;
+};
+
+template <typename T>
+__device__ __forceinline__ void draw(const RunArgs& a, int64_t chain, uint64_t pass_idx, int pass_in_call, int nsites,
+                                     int& site, T& u) {
+    if (a.replay) {
+        site = a.sites[(int64_t)pass_in_call * a.B + chain] - 1;
+        u = ((const T*)a.uniforms)[(int64_t)pass_in_call * a.B + chain];
+    } else {
+        uint64_t gid = (uint64_t)(a.chain_offset + chain);
+        Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+        uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)pass_idx, (uint32_t)(pass_idx >> 32)};
+        ph.gen(c);
+        site = (int)(((uint64_t)c[0] * (uint64_t)nsites) >> 32);
+        u = uniform01<T>(c[1], c[2]);
+    }
+}
+
+// ---- RBM / RBMSplit -------------------------------------------------------------------
+template <typename E, int ACT, bool DOUBLED>
+__global__ void sampler_rbm_kernel(const E* __restrict__ par, uint64_t* __restrict__ st_row, uint64_t* __restrict__ st_col,
+                                   RunArgs a) {
+    typedef typename elem_traits<E>::real T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int64_t chain = blockIdx.x * (int64_t)wpb + warp;
+    if (chain >= a.B) return;
+    const int N = a.N, M = a.M, W64 = (N + 63) >> 6;
+    E* th = (E*)smem_raw + (size_t)warp * 4 * M;
+    E* fk = th + M;
+    E* tth = fk + M;
+    E* tf = tth + M;
+    const int64_t off_b = DOUBLED ? 2 * N : N;
+    const E* __restrict__ Wr = par + off_b + M;
+    const E* __restrict__ Wc = Wr + (int64_t)M * N;
+    uint64_t rb[MAXW], cb[MAXW];
+#pragma unroll
+    for (int w = 0; w < MAXW; w++) {
+        rb[w] = w < W64 ? st_row[chain * W64 + w] : 0ull;
+        cb[w] = (DOUBLED && w < W64) ? st_col[chain * W64 + w] : 0ull;
+    }
+    const int nsites = DOUBLED ? 2 * N : N;
+    unsigned nacc = 0;
+    const int nsteps = a.burn + a.L;
+    for (int step = 0; step < nsteps; step++) {
+        // refresh theta from the configuration (bounds incremental round-off drift)
+        for (int k = lane; k < M; k += 32) {
+            E t = par[off_b + k];
+            for (int j = 0; j < N; j++) {
+                t += rscale(digit_value<T>(a.hilb, get_bit(rb, j)), Wr[k + (int64_t)M * j]);
+                if (DOUBLED) t += rscale(digit_value<T>(a.hilb, get_bit(cb, j)), Wc[k + (int64_t)M * j]);
+            }
+            E f, d;
+            act_eval<ACT>(t, f, d);
+            th[k] = t; fk[k] = f;
+        }
+        __syncwarp();
+        for (int ps = 0; ps < a.passes; ps++) {
+            int pic = step * a.passes + ps;
+            int site; T u;
+            draw<T>(a, chain, a.pass_base + (uint64_t)pic, pic, nsites, site, u);
+            const bool col = DOUBLED && site >= N;
+            const int j = col ? site - N : site;
+            const T dv = flip_delta<T>(a.hilb, get_bit(col ? cb : rb, j));
+            const E* __restrict__ wj = (col ? Wc : Wr) + (int64_t)M * j;
+            E part = make_zero<E>();
+            for (int k = lane; k < M; k += 32) {
+                E t = th[k] + rscale(dv, wj[k]);
+                E f, d;
+                act_eval<ACT>(t, f, d);
+                part += f - fk[k];
+                tth[k] = t; tf[k] = f;
+            }
+            part = warp_sum(part);
+            part += rscale(dv, par[(col ? N : 0) + j]);
+            const T dlp = T(2) * real_part(part);
+            const bool acc = (u - m_exp(dlp)) < T(0);
+            if (acc) {
+                for (int k = lane; k < M; k += 32) { th[k] = tth[k]; fk[k] = tf[k]; }
+                if (col) cb[j >> 6] ^= 1ull << (j & 63); else rb[j >> 6] ^= 1ull << (j & 63);
+                nacc++;
+            }
+            __syncwarp();
+            if (a.replay && a.accept_out && lane == 0) a.accept_out[(int64_t)pic * a.B + chain] = acc ? 1 : 0;
+        }
+        if (step >= a.burn && a.out_prow && lane == 0) {
+            int64_t o = ((int64_t)(step - a.burn) * a.B + chain) * W64;
+            for (int w = 0; w < W64; w++) { a.out_prow[o + w] = rb[w]; if (DOUBLED && a.out_pcol) a.out_pcol[o + w] = cb[w]; }
+        }
+    }
+    if (lane == 0) {
+        for (int w = 0; w < W64; w++) { st_row[chain * W64 + w] = rb[w]; if (DOUBLED) st_col[chain * W64 + w] = cb[w]; }
+        if (nacc) atomicAdd(a.accepted, (unsigned long long)nacc);
+    }
+}
+
+// ---- NDM ------------------------------------------------------------------------------
+// log p = 2 Re log rho = 2 [Gamma_lambda + Re sum_a f(Pi_a)]: the mu hidden layer only enters the
+// phase, so the sampler tracks the lambda layer (on sigma and sigma') and the ancilla layer only.
+// per warp: Pi[A], fPi[A], tentative Pi/fPi [A] (complex); th[2M] (side*M + k), f[2M], tentative th/f [M]
+template <typename T, int ACT>
+__global__ void sampler_ndm_kernel(const T* __restrict__ par, uint64_t* __restrict__ st_row, uint64_t* __restrict__ st_col,
+                                   RunArgs a) {
+    typedef cx<T> C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int64_t chain = blockIdx.x * (int64_t)wpb + warp;
+    if (chain >= a.B) return;
+    const int N = a.N, M = a.M, A = a.A, W64 = (N + 63) >> 6;
+    const size_t per_warp = (size_t)(6 * M) * sizeof(T) + (size_t)(4 * A) * sizeof(C);
+    unsigned char* base = smem_raw + (size_t)warp * per_warp;
+    C* pi0 = (C*)base;            // [A]
+    C* fpi = pi0 + A;
+    C* tpi = fpi + A;
+    C* tfpi = tpi + A;
+    T* th = (T*)(tfpi + A);       // [2M]
+    T* fk = th + 2 * M;           // [2M]
+    T* tth = fk + 2 * M;          // [M]
+    T* tf = tth + M;              // [M]
+    const int64_t MN = (int64_t)M * N, AN = (int64_t)A * N;
+    const int64_t o_wmu = N + M, o_umu = o_wmu + MN, o_blam = o_umu + AN,
+                  o_hlam = o_blam + N, o_dlam = o_hlam + M, o_wlam = o_dlam + A, o_ulam = o_wlam + MN;
+    const T half = T(0.5);
+    uint64_t rb[MAXW], cb[MAXW];
+#pragma unroll
+    for (int w = 0; w < MAXW; w++) {
+        rb[w] = w < W64 ? st_row[chain * W64 + w] : 0ull;
+        cb[w] = w < W64 ? st_col[chain * W64 + w] : 0ull;
+    }
+    unsigned nacc = 0;
+    const int nsteps = a.burn + a.L;
+    for (int step = 0; step < nsteps; step++) {
+        for (int k = lane; k < M; k += 32) {
+            const T* __restrict__ w = par + o_wlam + k;
+            T t = par[o_hlam + k], tp = t;
+            for (int j = 0; j < N; j++) {
+                T wv = w[(int64_t)M * j];
+                t += wv * digit_value<T>(a.hilb, get_bit(rb, j));
+                tp += wv * digit_value<T>(a.hilb, get_bit(cb, j));
+            }
+            T f, d, fp, dp;
+            act_eval<ACT>(t, f, d);
+            act_eval<ACT>(tp, fp, dp);
+            th[k] = t; fk[k] = f; th[M + k] = tp; fk[M + k] = fp;
+        }
+        for (int q = lane; q < A; q += 32) {
+            T pr = par[o_dlam + q], pim = T(0);
+            for (int j = 0; j < N; j++) {
+                T x = digit_value<T>(a.hilb, get_bit(rb, j)), y = digit_value<T>(a.hilb, get_bit(cb, j));
+                pr += half * par[o_ulam + q + (int64_t)A * j] * (x + y);
+                pim += half * par[o_umu + q + (int64_t)A * j] * (x - y);
+            }
+            C f, d;
+            act_eval<ACT>(C(pr, pim), f, d);
+            pi0[q] = C(pr, pim); fpi[q] = f;
+        }
+        __syncwarp();
+        for (int ps = 0; ps < a.passes; ps++) {
+            int pic = step * a.passes + ps;
+            int site; T u;
+            draw<T>(a, chain, a.pass_base + (uint64_t)pic, pic, 2 * N, site, u);
+            const bool col = site >= N;
+            const int j = col ? site - N : site;
+            const T dv = flip_delta<T>(a.hilb, get_bit(col ? cb : rb, j));
+            const int so = col ? M : 0;
+            T part = T(0);
+            for (int k = lane; k < M; k += 32) {
+                T t = th[so + k] + dv * par[o_wlam + k + (int64_t)M * j];
+                T f, d;
+                act_eval<ACT>(t, f, d);
+                part += half * (f - fk[so + k]);
+                tth[k] = t; tf[k] = f;
+            }
+            for (int q = lane; q < A; q += 32) {
+                C t = pi0[q];
+                T hd = half * dv;
+                t.re += hd * par[o_ulam + q + (int64_t)A * j];
+                t.im += (col ? -hd : hd) * par[o_umu + q + (int64_t)A * j];
+                C f, d;
+                act_eval<ACT>(t, f, d);
+                part += f.re - fpi[q].re;
+                tpi[q] = t; tfpi[q] = f;
+            }
+            part = warp_sum(part);
+            part += half * dv * par[o_blam + j];
+            const T dlp = T(2) * part;
+            const bool acc = (u - m_exp(dlp)) < T(0);
+            if (acc) {
+                for (int k = lane; k < M; k += 32) { th[so + k] = tth[k]; fk[so + k] = tf[k]; }
+                for (int q = lane; q < A; q += 32) { pi0[q] = tpi[q]; fpi[q] = tfpi[q]; }
+                if (col) cb[j >> 6] ^= 1ull << (j & 63); else rb[j >> 6] ^= 1ull << (j & 63);
+                nacc++;
+            }
+            __syncwarp();
+            if (a.replay && a.accept_out && lane == 0) a.accept_out[(int64_t)pic * a.B + chain] = acc ? 1 : 0;
+        }
+        if (step >= a.burn && a.out_prow && lane == 0) {
+            int64_t o = ((int64_t)(step - a.burn) * a.B + chain) * W64;
+            for (int w = 0; w < W64; w++) { a.out_prow[o + w] = rb[w]; if (a.out_pcol) a.out_pcol[o + w] = cb[w]; }
+        }
+    }
+    if (lane == 0) {
+        for (int w = 0; w < W64; w++) { st_row[chain * W64 + w] = rb[w]; st_col[chain * W64 + w] = cb[w]; }
+        if (nacc) atomicAdd(a.accepted, (unsigned long long)nacc);
+    }
+}
+
+template <typename E, int ACT, bool DOUBLED>
+int launch_sampler_rbm(nq_sampler_t s, const RunArgs& a) {
+    nq_machine_t m = s->m;
+    nq_ctx_t ctx = m->ctx;
+    size_t per_warp = (size_t)4 * m->M * sizeof(E);
+    int wpb = 8;
+    while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
+    size_t smem = per_warp * wpb;
+    if (smem > ctx->smem_optin) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "sampler needs %zu B shared memory per chain", per_warp);
+    auto kern = sampler_rbm_kernel<E, ACT, DOUBLED>;
+    NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = (unsigned)((s->B + wpb - 1) / wpb);
+    NQ_LAUNCH(ctx, kern, grid, wpb * 32, smem, (const E*)m->params, s->prow, s->pcol, a);
+    return NQ_OK;
+}
+
+template <typename T, int ACT>
+int launch_sampler_ndm(nq_sampler_t s, const RunArgs& a) {
+    nq_machine_t m = s->m;
+    nq_ctx_t ctx = m->ctx;
+    size_t per_warp = (size_t)6 * m->M * sizeof(T) + (size_t)4 * m->A * sizeof(cx<T>);
+    int wpb = 8;
+    while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
+    size_t smem = per_warp * wpb;
+    if (smem > ctx->smem_optin) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "sampler needs %zu B shared memory per chain", per_warp);
+    auto kern = sampler_ndm_kernel<T, ACT>;
+    NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = (unsigned)((s->B + wpb - 1) / wpb);
+    NQ_LAUNCH(ctx, kern, grid, wpb * 32, smem, (const T*)m->params, s->prow, s->pcol, a);
+    return NQ_OK;
+}
+
+template <typename E>
+int dispatch_sampler_rbm(nq_sampler_t s, const RunArgs& a) {
+    nq_machine_t m = s->m;
+    if (m->kind == NQ_RBMSPLIT) return launch_sampler_rbm<E, NQ_SOFTPLUS, true>(s, a);
+    if (m->act == NQ_SOFTPLUS) return launch_sampler_rbm<E, NQ_SOFTPLUS, false>(s, a);
+    return launch_sampler_rbm<E, NQ_LOGCOSH, false>(s, a);
+}
+
+int run_sampler(nq_sampler_t s, const RunArgs& a) {
+    nq_machine_t m = s->m;
+    if (m->N > 64 * MAXW) return nq_fail(m->ctx, NQ_ERR_UNSUPPORTED, "sampler supports N <= %d", 64 * MAXW);
+    if (m->kind == NQ_NDM) {
+        if (m->dtype == NQ_F64)
+            return m->act == NQ_SOFTPLUS ? launch_sampler_ndm<double, NQ_SOFTPLUS>(s, a) : launch_sampler_ndm<double, NQ_LOGCOSH>(s, a);
+        return m->act == NQ_SOFTPLUS ? launch_sampler_ndm<float, NQ_SOFTPLUS>(s, a) : launch_sampler_ndm<float, NQ_LOGCOSH>(s, a);
+    }
+    switch (m->dtype) {
+        case NQ_F32: return dispatch_sampler_rbm<float>(s, a);
+        case NQ_F64: return dispatch_sampler_rbm<double>(s, a);
+        case NQ_C64: return dispatch_sampler_rbm<cxf>(s, a);
+        default: return dispatch_sampler_rbm<cxd>(s, a);
+    }
+}
+
+RunArgs base_args(nq_sampler_t s) {
+    RunArgs a;
+    memset(&a, 0, sizeof a);
+    nq_machine_t m = s->m;
+    a.B = s->B; a.N = m->N; a.M = m->M; a.A = m->A; a.hilb = (int)m->hilb; a.passes = s->passes;
+    a.seed = s->seed; a.pass_base = s->pass_base; a.chain_offset = s->chain_offset; a.accepted = s->accepted;
+    return a;
+}
+
+}  // namespace
+
+extern "C" int nq_sampler_create(nq_machine_t m, int64_t B, int passes, uint64_t seed, int64_t chain_offset,
+                                 nq_sampler_t* out) {
+    if (!m || !out) return NQ_ERR_ARG;
+    *out = nullptr;
+    nq_ctx_t ctx = m->ctx;
+    if (B <= 0 || passes <= 0) return nq_fail(ctx, NQ_ERR_ARG, "B and passes must be positive");
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    nq_sampler_t s = new nq_sampler_s();
+    s->m = m; s->B = B;
+    s->passes = (passes % 2 == 0) ? passes + 1 : passes;   // Metropolis.jl:30-38
+    s->seed = seed; s->chain_offset = chain_offset; s->pass_base = 0; s->passes_done = 0;
+    s->prow = s->pcol = nullptr; s->accepted = nullptr;
+    size_t pbytes = (size_t)B * nq_words(m->N) * 8;
+    bool ok = cudaMalloc((void**)&s->prow, pbytes) == cudaSuccess &&
+              (!m->doubled() || cudaMalloc((void**)&s->pcol, pbytes) == cudaSuccess) &&
+              cudaMalloc((void**)&s->accepted, 8) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        cudaFree(s->prow); cudaFree(s->pcol); cudaFree(s->accepted);
+        delete s;
+        return nq_fail(ctx, NQ_ERR_ALLOC, "sampler allocation failed");
+    }
+    cudaMemsetAsync(s->prow, 0, pbytes, ctx->stream);
+    if (s->pcol) cudaMemsetAsync(s->pcol, 0, pbytes, ctx->stream);
+    cudaMemsetAsync(s->accepted, 0, 8, ctx->stream);
+    *out = s;
+    return NQ_OK;
+}
+
+extern "C" int nq_sampler_destroy(nq_sampler_t s) {
+    if (!s) return NQ_ERR_ARG;
+    cudaSetDevice(s->m->ctx->device);
+    cudaStreamSynchronize(s->m->ctx->stream);
+    cudaFree(s->prow); cudaFree(s->pcol); cudaFree(s->accepted);
+    delete s;
+    return NQ_OK;
+}
+
+extern "C" int nq_sampler_set_state(nq_sampler_t s, const void* srow, const void* scol, nq_dtype sdtype) {
+    if (!s || !srow) return NQ_ERR_ARG;
+    nq_machine_t m = s->m;
+    nq_ctx_t ctx = m->ctx;
+    if (m->doubled() != (scol != nullptr)) return nq_fail(ctx, NQ_ERR_ARG, "row/col configuration mismatch");
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    NqStage st(ctx);
+    size_t fbytes = (size_t)s->B * m->N * nq_dtype_size(sdtype);
+    const void* dr = st.in(SL_IN0, srow, fbytes);
+    const void* dc = scol ? st.in(SL_IN1, scol, fbytes) : nullptr;
+    if (st.status != NQ_OK) return st.status;
+    NQ_CHECK(nq_pack_device(ctx, m->hilb, m->N, s->B, dr, sdtype, s->prow));
+    if (scol) NQ_CHECK(nq_pack_device(ctx, m->hilb, m->N, s->B, dc, sdtype, s->pcol));
+    NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NQ_OK;
+}
+
+extern "C" int nq_sampler_get_state(nq_sampler_t s, void* srow, void* scol, nq_dtype sdtype) {
+    if (!s || !srow) return NQ_ERR_ARG;
+    nq_machine_t m = s->m;
+    nq_ctx_t ctx = m->ctx;
+    if (m->doubled() != (scol != nullptr)) return nq_fail(ctx, NQ_ERR_ARG, "row/col configuration mismatch");
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    NqStage st(ctx);
+    size_t fbytes = (size_t)s->B * m->N * nq_dtype_size(sdtype);
+    void* dr = st.out(SL_OUT0, srow, fbytes);
+    void* dc = scol ? st.out(SL_OUT1, scol, fbytes) : nullptr;
+    if (st.status != NQ_OK) return st.status;
+    NQ_CHECK(nq_unpack_device(ctx, m->hilb, m->N, s->B, s->prow, dr, sdtype));
+    if (scol) NQ_CHECK(nq_unpack_device(ctx, m->hilb, m->N, s->B, s->pcol, dc, sdtype));
+    return st.finish();
+}
+
+extern "C" int nq_sampler_randomize(nq_sampler_t s) {
+    if (!s) return NQ_ERR_ARG;
+    nq_machine_t m = s->m;
+    nq_ctx_t ctx = m->ctx;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    int W64 = nq_words(m->N);
+    int64_t n = s->B * W64;
+    NQ_LAUNCH(ctx, randomize_kernel, (unsigned)((n + 255) / 256), 256, 0, s->prow, s->pcol, s->B, m->N, W64, s->seed,
+              s->chain_offset, s->pass_base);
+    return NQ_OK;
+}
+
+extern "C" int nq_sampler_replay(nq_sampler_t s, const int32_t* sites, const void* uniforms, uint8_t* accept_out) {
+    if (!s || !sites || !uniforms) return NQ_ERR_ARG;
+    nq_machine_t m = s->m;
+    nq_ctx_t ctx = m->ctx;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    NqStage st(ctx);
+    size_t n = (size_t)s->passes * s->B;
+    RunArgs a = base_args(s);
+    a.replay = 1; a.burn = 0; a.L = 1;
+    a.sites = (const int32_t*)st.in(SL_IN0, sites, n * 4);
+    a.uniforms = st.in(SL_IN1, uniforms, n * nq_dtype_size(nq_real_of(m->dtype)));
+    a.accept_out = accept_out ? (uint8_t*)st.out(SL_OUT0, accept_out, n) : nullptr;
+    if (st.status != NQ_OK) return st.status;
+    NQ_CHECK(run_sampler(s, a));
+    s->passes_done += (int64_t)n;
+    return st.finish();
+}
+
+extern "C" int nq_sampler_sample(nq_sampler_t s, int burn, int L, uint64_t* prow, uint64_t* pcol, void* srow,
+                                 void* scol, nq_dtype sdtype) {
+    if (!s || burn < 0 || L < 0) return NQ_ERR_ARG;
+    nq_machine_t m = s->m;
+    nq_ctx_t ctx = m->ctx;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (burn + L == 0) return NQ_OK;
+    NqStage st(ctx);
+    const int W64 = nq_words(m->N);
+    size_t pbytes = (size_t)(L ? L : 1) * s->B * W64 * 8;
+    size_t fbytes = (size_t)L * s->B * m->N * nq_dtype_size(sdtype);
+    RunArgs a = base_args(s);
+    a.replay = 0; a.burn = burn; a.L = L;
+    const bool want = L > 0 && (prow || srow);
+    if (want) {
+        a.out_prow = prow ? (uint64_t*)st.out(SL_OUT0, prow, pbytes) : (uint64_t*)nq_scratch(ctx, SL_W0, pbytes);
+        if (m->doubled()) a.out_pcol = pcol ? (uint64_t*)st.out(SL_OUT1, pcol, pbytes) : (uint64_t*)nq_scratch(ctx, SL_W1, pbytes);
+        if (!a.out_prow || (m->doubled() && !a.out_pcol)) return NQ_ERR_ALLOC;
+    }
+    void* dsr = (L > 0 && srow) ? st.out(SL_OUT2, srow, fbytes) : nullptr;
+    void* dsc = (L > 0 && scol && m->doubled()) ? st.out(SL_OUT3, scol, fbytes) : nullptr;
+    if (st.status != NQ_OK) return st.status;
+    NQ_CHECK(run_sampler(s, a));
+    s->pass_base += (uint64_t)(burn + L) * s->passes;
+    s->passes_done += (int64_t)(burn + L) * s->passes * s->B;
+    if (dsr) NQ_CHECK(nq_unpack_device(ctx, m->hilb, m->N, (int64_t)L * s->B, a.out_prow, dsr, sdtype));
+    if (dsc) NQ_CHECK(nq_unpack_device(ctx, m->hilb, m->N, (int64_t)L * s->B, a.out_pcol, dsc, sdtype));
+    return st.finish();
+}
+
+extern "C" int nq_sampler_counters(nq_sampler_t s, int64_t* passes_done, int64_t* passes_accepted) {
+    if (!s) return NQ_ERR_ARG;
+    nq_ctx_t ctx = s->m->ctx;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long acc = 0;
+    NQ_CUDA(ctx, cudaMemcpyAsync(&acc, s->accepted, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (passes_done) *passes_done = s->passes_done;
+    if (passes_accepted) *passes_accepted = (int64_t)acc;
+    return NQ_OK;
+}

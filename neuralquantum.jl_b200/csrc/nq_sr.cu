@@ -1,0 +1,1032 @@
+// nq_sr.cu -- K6-K9: gradient centring, force vector, S-matrix assembly, solve, parameter update.
+//
+//   K6  nq_center / nq_force_*      column means and weighted column sums over the [P, Ns] matrices
+//                                    (HBM-bound streaming passes, FP64 accumulation, fixed order)
+//   K7  nq_sr_setup                  S = Oc Oc^H / Ns as a split-K SYRK/HERK on the FP64 tensor path
+//                                    (mma.sync m8n8k4 f64 = DMMA; tcgen05 has no FP64 kind), lower
+//                                    tile triangle only, deterministic two-stage reduction
+//   K8  nq_sr_solve(_matfree)        blocked Cholesky (cuSOLVER-free) or CG (IterativeSolvers 0.8.1 rule)
+//   K9  nq_update                    w <- w - eta dw
+//
+// ref: IterativeInterface/Samplers/BaseIterativeSampler.jl:19-26, CostFun/BatchedValSampler.jl:97-115,
+//      CostFun/BatchedGradSampler.jl:99-118, Algorithms/SR/SRDirect.jl:26-90, SRIterative.jl:71-153,
+//      SR_notfull.jl:47-148, Optimisers/rules.jl:11-17, utils/stats.jl:26-50.
+#include "nq_internal.cuh"
+#include <algorithm>
+
+int nq_allreduce_device(nq_ctx_t ctx, void* buf, int64_t n, nq_dtype dtype, bool mean);
+
+namespace {
+
+// ======================================================================================
+// K6: column sums over samples.  X is [P, Ns] (leading dimension ld) of E; thread = parameter
+// (coalesced), gridDim.y slices the samples; partials are summed in a fixed order.
+//   out[k] = scale * sum_s w[s] * (CONJ ? conj(X[k,s]) : X[k,s])        (w == nullptr: w = 1)
+// ======================================================================================
+template <typename E, bool CONJ>
+__global__ void colsum_partial_kernel(const E* __restrict__ X, int64_t ld, int64_t P, int64_t Ns,
+                                      const cx<typename elem_traits<E>::real>* __restrict__ w,
+                                      cxd* __restrict__ partial) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= P) return;
+    int64_t per = (Ns + gridDim.y - 1) / gridDim.y;
+    int64_t s0 = blockIdx.y * per, s1 = s0 + per < Ns ? s0 + per : Ns;
+    double ar = 0.0, ai = 0.0;
+    for (int64_t s = s0; s < s1; s++) {
+        E x = X[k + ld * s];
+        double xr = (double)real_part(x), xi = (double)imag_part(x);
+        if (CONJ) xi = -xi;
+        if (w) {
+            double wr = (double)w[s].re, wi = (double)w[s].im;
+            ar += wr * xr - wi * xi;
+            ai += wr * xi + wi * xr;
+        } else { ar += xr; ai += xi; }
+    }
+    partial[blockIdx.y * P + k] = cxd(ar, ai);
+}
+
+template <typename E>   // out of E-compatible complex/real type, fixed-order reduction of the slices
+__global__ void colsum_final_kernel(const cxd* __restrict__ partial, int nslice, int64_t P, double scale,
+                                    cxd* __restrict__ out) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= P) return;
+    double ar = 0.0, ai = 0.0;
+    for (int i = 0; i < nslice; i++) { ar += partial[i * P + k].re; ai += partial[i * P + k].im; }
+    out[k] = cxd(ar * scale, ai * scale);
+}
+
+template <typename E, bool CONJ>
+int colsum(nq_ctx_t ctx, const void* X, int64_t ld, int64_t P, int64_t Ns, const void* w, double scale, cxd* out) {
+    int nslice = (int)std::min<int64_t>(std::max<int64_t>(1, Ns / 256), 4 * (int64_t)ctx->num_sms * 8 / std::max<int64_t>(1, (P + 127) / 128));
+    nslice = std::max(1, std::min(nslice, 1024));
+    cxd* partial = (cxd*)nq_scratch(ctx, SL_W5, (size_t)nslice * P * sizeof(cxd));
+    if (!partial) return NQ_ERR_ALLOC;
+    dim3 grid((unsigned)((P + 127) / 128), (unsigned)nslice);
+    NQ_LAUNCH(ctx, (colsum_partial_kernel<E, CONJ>), grid, 128, 0, (const E*)X, ld, P, Ns,
+              (const cx<typename elem_traits<E>::real>*)w, partial);
+    NQ_LAUNCH(ctx, colsum_final_kernel<E>, (unsigned)((P + 255) / 256), 256, 0, partial, nslice, P, scale, out);
+    return NQ_OK;
+}
+
+template <bool CONJ>
+int colsum_dispatch(nq_ctx_t ctx, nq_dtype dtype, const void* X, int64_t ld, int64_t P, int64_t Ns, const void* w,
+                    double scale, cxd* out) {
+    switch (dtype) {
+        case NQ_F32: return colsum<float, CONJ>(ctx, X, ld, P, Ns, w, scale, out);
+        case NQ_F64: return colsum<double, CONJ>(ctx, X, ld, P, Ns, w, scale, out);
+        case NQ_C64: return colsum<cxf, CONJ>(ctx, X, ld, P, Ns, w, scale, out);
+        default: return colsum<cxd, CONJ>(ctx, X, ld, P, Ns, w, scale, out);
+    }
+}
+
+template <typename E>
+__global__ void subtract_avg_kernel(E* __restrict__ X, int64_t ld, int64_t P, int64_t Ns, const cxd* __restrict__ avg) {
+    typedef typename elem_traits<E>::real T;
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= P) return;
+    cxd a = avg[k];
+    for (int64_t s = blockIdx.y; s < Ns; s += gridDim.y) {
+        E x = X[k + ld * s];
+        if (elem_traits<E>::is_complex) {
+            cx<T>* px = (cx<T>*)&X[k + ld * s];
+            *px = cx<T>((T)((double)real_part(x) - a.re), (T)((double)imag_part(x) - a.im));
+        } else {
+            T* px = (T*)&X[k + ld * s];
+            *px = (T)((double)real_part(x) - a.re);
+        }
+    }
+}
+
+// convert a cxd vector to dtype (real dtypes take the real part)
+__global__ void convert_from_cxd_kernel(const cxd* __restrict__ in, void* __restrict__ out, int64_t n, int dtype, int conj_in) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cxd v = in[i];
+    if (conj_in) v.im = -v.im;
+    switch (dtype) {
+        case NQ_F32: ((float*)out)[i] = (float)v.re; break;
+        case NQ_F64: ((double*)out)[i] = v.re; break;
+        case NQ_C64: ((cxf*)out)[i] = cxf((float)v.re, (float)v.im); break;
+        default: ((cxd*)out)[i] = v; break;
+    }
+}
+__global__ void convert_to_cxd_kernel(const void* __restrict__ in, cxd* __restrict__ out, int64_t n, int dtype) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    switch (dtype) {
+        case NQ_F32: out[i] = cxd((double)((const float*)in)[i], 0.0); break;
+        case NQ_F64: out[i] = cxd(((const double*)in)[i], 0.0); break;
+        case NQ_C64: { cxf v = ((const cxf*)in)[i]; out[i] = cxd((double)v.re, (double)v.im); } break;
+        default: out[i] = ((const cxd*)in)[i]; break;
+    }
+}
+
+// sum_s |L_s|^2 (single block, fixed order)
+template <typename T>
+__global__ void abs2_sum_kernel(const cx<T>* __restrict__ L, int64_t n, double* __restrict__ out) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { double r = (double)L[i].re, m = (double)L[i].im; acc += r * r + m * m; }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { double s = 0.0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w]; *out = s; }
+}
+
+// gradC_k = conj(x_k) - cost * avg_k' ...: out = a - c*b (complex vectors, c real on device)
+__global__ void force_liouv_finish_kernel(const cxd* __restrict__ lg, const cxd* __restrict__ avg, const double* __restrict__ sumabs2,
+                                          double inv_ns, int64_t P, cxd* __restrict__ out) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= P) return;
+    double C = *sumabs2 * inv_ns;
+    // lg_k = (1/Ns) sum_s conj(L_s) gL_ks ; F_k = lg_k - C avg_k
+    out[k] = cxd(lg[k].re - C * avg[k].re, lg[k].im - C * avg[k].im);
+}
+
+// ======================================================================================
+// K7: SYRK / HERK on DMMA.  X viewed as reals: X[k, s, c] at Xr[(k*NC + c) + ldr*s].
+//   mode 0: C[k,l] = sum_{s,c} X[k,s,c] X[l,s,c]                       (real part of O O^H)
+//   mode 1: C[k,l] = sum_s X[k,s,0] X[l,s,1] - X[k,s,1] X[l,s,0]       (imag part of conj(O O^H))
+// CTA tile 128x128, 8 warps as 2(m) x 4(n), warp tile 64x32 = 8x4 mma tiles, K chunk = KS samples.
+// ======================================================================================
+constexpr int TS = 128;       // tile size
+constexpr int KS = 8;         // samples per chunk
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <typename T, int NC>
+__global__ void __launch_bounds__(256, 1)
+syrk_dmma_kernel(const T* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, int ntile, int nsplit, int mode,
+                 double* __restrict__ Wk /* [nsplit][Ppad*Ppad] col-major, Ppad = ntile*TS */) {
+    constexpr int LD = TS * NC + (NC == 2 ? 8 : 4);     // padded row (one sample) of a tile, in doubles
+    constexpr int PER = TS * NC * KS / 256;             // reals per thread per tile per chunk
+    extern __shared__ __align__(16) double smem[];
+    // decode lower-triangular tile index
+    int t = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+    while (ti * (ti + 1) / 2 > t) ti--;
+    int tj = t - ti * (ti + 1) / 2;
+    const bool diag = ti == tj;
+    const int split = blockIdx.y;
+    const int64_t nchunk_tot = (Ns + KS - 1) / KS;
+    const int64_t cper = (nchunk_tot + nsplit - 1) / nsplit;
+    const int64_t c_begin = split * cper, c_end = std::min<int64_t>(nchunk_tot, c_begin + cper);
+
+    double* As[2] = {smem, smem + 2 * KS * LD};
+    double* Bs[2] = {smem + KS * LD, smem + 3 * KS * LD};
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tq = lane & 3;
+    const int wm = warp & 1, wn = warp >> 1;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    T ra[PER], rbv[PER];
+    const int64_t rowA = (int64_t)ti * TS * NC, rowB = (int64_t)tj * TS * NC, PR = P * NC;
+
+    auto gload = [&](int64_t chunk) {
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            int e = tid + 256 * i;               // e = s * (TS*NC) + r
+            int s = e / (TS * NC), r = e - s * (TS * NC);
+            int64_t smp = chunk * KS + s;
+            bool okA = smp < Ns && rowA + r < PR, okB = smp < Ns && rowB + r < PR;
+            ra[i] = okA ? Xr[rowA + r + ldr * smp] : T(0);
+            if (!diag) rbv[i] = okB ? Xr[rowB + r + ldr * smp] : T(0);
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            int e = tid + 256 * i;
+            int s = e / (TS * NC), r = e - s * (TS * NC);
+            As[buf][s * LD + r] = (double)ra[i];
+            if (!diag) Bs[buf][s * LD + r] = (double)rbv[i];
+        }
+    };
+
+    if (c_begin < c_end) {
+        gload(c_begin);
+        sstore(0);
+    }
+    __syncthreads();
+    for (int64_t c = c_begin; c < c_end; c++) {
+        const int buf = (int)((c - c_begin) & 1);
+        if (c + 1 < c_end) gload(c + 1);
+        const double* A = As[buf];
+        const double* Bm = diag ? As[buf] : Bs[buf];
+#pragma unroll
+        for (int k4 = 0; k4 < KS * NC / 4; k4++) {
+            // logical k index kk = 4*k4 + tq -> (sample, component)
+            const int kk = 4 * k4 + tq;
+            const int s = NC == 2 ? (kk >> 1) : kk;
+            const int cc = NC == 2 ? (kk & 1) : 0;
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = A[s * LD + (wm * 64 + i * 8 + g) * NC + cc];
+            if (mode == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) b[j] = Bm[s * LD + (wn * 32 + j * 8 + g) * NC + cc];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    double v = Bm[s * LD + (wn * 32 + j * 8 + g) * NC + (1 - cc)];
+                    b[j] = cc ? -v : v;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        if (c + 1 < c_end) sstore(buf ^ 1);
+        __syncthreads();
+    }
+    const int64_t Ppad = (int64_t)ntile * TS;
+    double* W = Wk + (size_t)split * Ppad * Ppad;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int64_t row = (int64_t)ti * TS + wm * 64 + i * 8 + g;
+            int64_t col = (int64_t)tj * TS + wn * 32 + j * 8 + 2 * tq;
+            W[row + Ppad * col] = acc[i][j][0];
+            W[row + Ppad * (col + 1)] = acc[i][j][1];
+        }
+}
+
+// S[k,l] from the lower tile triangle: sum the splits in order, scale, mirror (Hermitian)
+// out_complex: S complex (re from Wre, im from Wim); else real.
+template <typename TS_>
+__global__ void syrk_finalize_kernel(const double* __restrict__ Wre, const double* __restrict__ Wim, int nsplit,
+                                     int64_t Ppad, int64_t P, double scale, int out_complex, TS_* __restrict__ S) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t l = blockIdx.y;
+    if (k >= P || l >= P) return;
+    bool lower = (k / TS) >= (l / TS);
+    int64_t r = lower ? k : l, c = lower ? l : k;
+    double re = 0.0, im = 0.0;
+    for (int s = 0; s < nsplit; s++) {
+        re += Wre[(size_t)s * Ppad * Ppad + r + Ppad * c];
+        if (Wim) im += Wim[(size_t)s * Ppad * Ppad + r + Ppad * c];
+    }
+    if (!lower) im = -im;
+    if (out_complex) { S[2 * (k + P * l)] = (TS_)(re * scale); S[2 * (k + P * l) + 1] = (TS_)(im * scale); }
+    else S[k + P * l] = (TS_)(re * scale);
+}
+
+template <typename T, int NC>
+int launch_syrk(nq_ctx_t ctx, const void* X, int64_t ldr, int64_t P, int64_t Ns, int ntile, int nsplit, int mode, double* W) {
+    constexpr int LD = TS * NC + (NC == 2 ? 8 : 4);
+    size_t smem = (size_t)4 * KS * LD * sizeof(double);
+    auto kern = syrk_dmma_kernel<T, NC>;
+    NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)(ntile * (ntile + 1) / 2), (unsigned)nsplit);
+    NQ_LAUNCH(ctx, kern, grid, 256, smem, (const T*)X, ldr, P, Ns, ntile, nsplit, mode, W);
+    return NQ_OK;
+}
+
+// ======================================================================================
+// K8: blocked Cholesky  A = L L^H  (lower, column-major, in place) on double or complex double
+// ======================================================================================
+constexpr int NB = 32;
+
+__device__ __forceinline__ double mulc(double a, double b) { return a * b; }            // a * conj(b)
+__device__ __forceinline__ cxd mulc(cxd a, cxd b) { return cxd(a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im); }
+__device__ __forceinline__ double divr(double a, double r) { return a / r; }
+__device__ __forceinline__ cxd divr(cxd a, double r) { return cxd(a.re / r, a.im / r); }
+
+// factor the diagonal block (held in shared memory Lb[NB][NB+1], row r = lane) with one warp
+template <typename E>
+__device__ void potf2_warp(E (*Lb)[NB + 1], int nb, int64_t j0, int* info) {
+    const int r = threadIdx.x & 31;
+    for (int c = 0; c < nb; c++) {
+        double d = real_part(Lb[c][c]);
+        if (!(d > 0.0)) { if (r == 0) atomicCAS(info, -1, (int)(j0 + c)); d = 1.0; }
+        double l = sqrt(d);
+        __syncwarp();
+        if (r == c) Lb[c][c] = from_real<E, double>(l);
+        if (r > c && r < nb) Lb[r][c] = divr(Lb[r][c], l);
+        __syncwarp();
+        if (r > c && r < nb) {
+            E lrc = Lb[r][c];
+            for (int c2 = c + 1; c2 <= r; c2++) Lb[r][c2] -= mulc(lrc, Lb[c2][c]);
+        }
+        __syncwarp();
+    }
+}
+
+// panel: every CTA factors the diagonal block redundantly in shared memory; CTA 0 writes it back;
+// all CTAs apply X = A[i, j0:j0+nb] L_jj^{-H} to their rows below the block.
+template <typename E>
+__global__ void chol_panel_kernel(E* __restrict__ A, int64_t P, int64_t j0, int nb, int* __restrict__ info) {
+    __shared__ E Lb[NB][NB + 1];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NB * NB; i += blockDim.x) {
+        int r = i % NB, c = i / NB;
+        Lb[r][c] = (r < nb && c < nb && c <= r) ? A[(j0 + r) + P * (j0 + c)] : make_zero<E>();
+    }
+    __syncthreads();
+    if (tid < 32) potf2_warp<E>(Lb, nb, j0, info);
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        for (int i = tid; i < NB * NB; i += blockDim.x) {
+            int r = i % NB, c = i / NB;
+            if (r < nb && c < nb) A[(j0 + r) + P * (j0 + c)] = c <= r ? Lb[r][c] : make_zero<E>();
+        }
+    }
+    int64_t row = j0 + nb + blockIdx.x * (int64_t)blockDim.x + tid;
+    if (row >= P) return;
+    E x[NB];
+#pragma unroll
+    for (int c = 0; c < NB; c++) x[c] = c < nb ? A[row + P * (j0 + c)] : make_zero<E>();
+#pragma unroll
+    for (int c = 0; c < NB; c++) {
+        if (c < nb) {
+            E v = x[c];
+#pragma unroll
+            for (int c2 = 0; c2 < NB; c2++) if (c2 < c) v -= mulc(x[c2], Lb[c][c2]);
+            x[c] = divr(v, real_part(Lb[c][c]));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NB; c++) if (c < nb) A[row + P * (j0 + c)] = x[c];
+}
+
+// trailing update C[i,l] -= sum_c X[i,c] conj(X[l,c]) on the lower tile triangle, 64x64 tiles, 4x4 per thread
+constexpr int KU = 16;
+template <typename E>
+__global__ void chol_update_kernel(E* __restrict__ A, int64_t P, int64_t j0, int nb) {
+    __shared__ E Xi[KU][64 + 1];
+    __shared__ E Xl[KU][64 + 1];
+    int t = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+    while (ti * (ti + 1) / 2 > t) ti--;
+    int tj = t - ti * (ti + 1) / 2;
+    const int64_t base = j0 + nb;
+    const int64_t i0 = base + (int64_t)ti * 64, l0 = base + (int64_t)tj * 64;
+    const int tid = threadIdx.x;
+    const int tr = tid % 16, tc = tid / 16;   // 16x16 threads, 4x4 each
+    E acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = make_zero<E>();
+    for (int kh = 0; kh < nb; kh += KU) {
+        for (int e = tid; e < KU * 64; e += blockDim.x) {
+            int r = e % 64, c = e / 64;
+            Xi[c][r] = (kh + c < nb && i0 + r < P) ? A[(i0 + r) + P * (j0 + kh + c)] : make_zero<E>();
+            Xl[c][r] = (kh + c < nb && l0 + r < P) ? A[(l0 + r) + P * (j0 + kh + c)] : make_zero<E>();
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < KU; c++) {
+            E xi[4], xl[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) { xi[a] = Xi[c][tr + 16 * a]; xl[a] = Xl[c][tc + 16 * a]; }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) acc[a][b] += mulc(xi[a], xl[b]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            int64_t i = i0 + tr + 16 * a, l = l0 + tc + 16 * b;
+            if (i < P && l < P && i >= l) A[i + P * l] -= acc[a][b];
+        }
+}
+
+template <typename E> __device__ __forceinline__ E mk(double re, double im);
+template <> __device__ __forceinline__ double mk<double>(double re, double) { return re; }
+template <> __device__ __forceinline__ cxd mk<cxd>(double re, double im) { return cxd(re, im); }
+template <typename E> __device__ __forceinline__ E bcast(E v, int src) {
+    return mk<E>(__shfl_sync(0xffffffffu, real_part(v), src), __shfl_sync(0xffffffffu, imag_part(v), src));
+}
+
+// forward L y = b (right-looking, coalesced row updates) then backward L^H x = y (left-looking,
+// coalesced column dot products); a single CTA walks the block columns.
+template <typename E>
+__global__ void chol_solve_kernel(const E* __restrict__ L, int64_t P, E* __restrict__ x) {
+    __shared__ E blk[NB];
+    __shared__ E Lb[NB][NB + 1];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    for (int64_t j0 = 0; j0 < P; j0 += NB) {
+        const int nb = (int)((P - j0) < NB ? (P - j0) : NB);
+        for (int i = tid; i < NB * NB; i += nt) {
+            int r = i % NB, c = i / NB;
+            Lb[r][c] = (r < nb && c < nb) ? L[(j0 + r) + P * (j0 + c)] : make_zero<E>();
+        }
+        __syncthreads();
+        if (warp == 0) {
+            E v = lane < nb ? x[j0 + lane] : make_zero<E>();
+            for (int c = 0; c < nb; c++) {
+                E yc = divr(bcast(v, c), real_part(Lb[c][c]));
+                if (lane == c) v = yc;
+                if (lane > c && lane < nb) v -= Lb[lane][c] * yc;
+            }
+            if (lane < nb) { x[j0 + lane] = v; blk[lane] = v; }
+        }
+        __syncthreads();
+        for (int64_t i = j0 + nb + tid; i < P; i += nt) {
+            E v = x[i];
+            for (int c = 0; c < nb; c++) v -= L[i + P * (j0 + c)] * blk[c];
+            x[i] = v;
+        }
+        __syncthreads();
+    }
+    const int64_t nblk = (P + NB - 1) / NB;
+    for (int64_t bi = nblk - 1; bi >= 0; bi--) {
+        const int64_t j0 = bi * NB;
+        const int nb = (int)((P - j0) < NB ? (P - j0) : NB);
+        for (int i = tid; i < NB * NB; i += nt) {
+            int r = i % NB, c = i / NB;
+            Lb[r][c] = (r < nb && c < nb) ? L[(j0 + r) + P * (j0 + c)] : make_zero<E>();
+        }
+        // rhs_c = y_c - sum_{r >= j0+nb} conj(L[r, j0+c]) x_r
+        for (int c = warp; c < nb; c += nw) {
+            E acc = make_zero<E>();
+            for (int64_t r = j0 + nb + lane; r < P; r += 32) acc += mulc(x[r], L[r + P * (j0 + c)]);
+            acc = warp_sum(acc);
+            if (lane == 0) blk[c] = x[j0 + c] - acc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            E v = lane < nb ? blk[lane] : make_zero<E>();
+            for (int c = nb - 1; c >= 0; c--) {
+                E xc = divr(bcast(v, c), real_part(Lb[c][c]));
+                if (lane == c) v = xc;
+                if (lane < c) v -= mulc(xc, Lb[c][lane]);   // conj(L[c][lane]) x_c
+            }
+            if (lane < nb) x[j0 + lane] = v;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename E>
+__global__ void add_diag_kernel(E* __restrict__ A, int64_t P, double eps) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < P) A[i + P * i] += from_real<E, double>(eps);
+}
+
+template <typename E>
+int cholesky_solve(nq_ctx_t ctx, E* A, int64_t P, E* x, int* dinfo) {
+    for (int64_t j0 = 0; j0 < P; j0 += NB) {
+        int nb = (int)std::min<int64_t>(NB, P - j0);
+        int64_t below = P - j0 - nb;
+        unsigned gp = (unsigned)std::max<int64_t>(1, (below + 127) / 128);
+        NQ_LAUNCH(ctx, chol_panel_kernel<E>, gp, 128, 0, A, P, j0, nb, dinfo);
+        if (below > 0) {
+            int64_t nt = (below + 63) / 64;
+            NQ_LAUNCH(ctx, chol_update_kernel<E>, (unsigned)(nt * (nt + 1) / 2), 256, 0, A, P, j0, nb);
+        }
+    }
+    NQ_LAUNCH(ctx, chol_solve_kernel<E>, 1, 1024, 0, (const E*)A, P, x);
+    return NQ_OK;
+}
+
+// ======================================================================================
+// CG on an explicit S (+ eps I) or matrix-free; vectors are E = double | cxd
+// ======================================================================================
+template <typename E>
+__global__ void gemv_partial_kernel(const E* __restrict__ S, int64_t P, const E* __restrict__ v, E* __restrict__ partial) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    int64_t per = (P + gridDim.y - 1) / gridDim.y;
+    int64_t j0 = blockIdx.y * per, j1 = j0 + per < P ? j0 + per : P;
+    E acc = make_zero<E>();
+    for (int64_t j = j0; j < j1; j++) acc += S[i + P * j] * v[j];
+    partial[blockIdx.y * P + i] = acc;
+}
+template <typename E>
+__global__ void gemv_final_kernel(const E* __restrict__ partial, int nslice, int64_t P, const E* __restrict__ v, double eps,
+                                  E* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    E acc = rscale(eps, v[i]);
+    for (int s = 0; s < nslice; s++) acc += partial[s * P + i];
+    out[i] = acc;
+}
+// out[0] = <a, b> = sum conj(a_i) b_i (single block, fixed order), as (re, im)
+template <typename E>
+__global__ void dot_kernel(const E* __restrict__ a, const E* __restrict__ b, int64_t n, double* __restrict__ out) {
+    __shared__ double red[64];
+    double ar = 0.0, ai = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        cxd p = mulc(to_cx(b[i]), to_cx(a[i]));
+        ar += p.re; ai += p.im;
+    }
+    ar = warp_sum(ar); ai = warp_sum(ai);
+    if ((threadIdx.x & 31) == 0) { red[2 * (threadIdx.x >> 5)] = ar; red[2 * (threadIdx.x >> 5) + 1] = ai; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sr = 0.0, si = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { sr += red[2 * w]; si += red[2 * w + 1]; }
+        out[0] = sr; out[1] = si;
+    }
+}
+// u = r + beta u
+template <typename E>
+__global__ void cg_update_u_kernel(E* __restrict__ u, const E* __restrict__ r, double beta, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) u[i] = r[i] + rscale(beta, u[i]);
+}
+// x += alpha u ; r -= alpha c    (alpha = res^2 / <u,c>, complex in general)
+template <typename E>
+__global__ void cg_update_xr_kernel(E* __restrict__ x, E* __restrict__ r, const E* __restrict__ u, const E* __restrict__ c,
+                                    double res2, const double* __restrict__ uc, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double dr = uc[0], di = uc[1], den = dr * dr + di * di;
+    cxd alpha(res2 * dr / den, -res2 * di / den);
+    cxd au = alpha * to_cx(u[i]), ac = alpha * to_cx(c[i]);
+    x[i] += mk<E>(au.re, au.im);
+    r[i] -= mk<E>(ac.re, ac.im);
+}
+
+// matrix-free pieces: t[s] = sum_k O[k,s] v_k   (one warp per sample)
+template <typename EO, typename EV>
+__global__ void ot_v_kernel(const EO* __restrict__ O, int64_t ld, int64_t P, int64_t Ns, const EV* __restrict__ v,
+                            cx<typename elem_traits<EO>::real>* __restrict__ t) {
+    typedef typename elem_traits<EO>::real T;
+    int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (s >= Ns) return;
+    double ar = 0.0, ai = 0.0;
+    for (int64_t k = lane; k < P; k += 32) {
+        cxd o = cxd((double)real_part(O[k + ld * s]), (double)imag_part(O[k + ld * s]));
+        cxd p = o * to_cx(v[k]);
+        ar += p.re; ai += p.im;
+    }
+    ar = warp_sum(ar); ai = warp_sum(ai);
+    if (lane == 0) t[s] = cx<T>((T)ar, (T)ai);
+}
+// out = eps v + (real ? Re(y) : y)
+template <typename E>
+__global__ void matfree_finish_kernel(const cxd* __restrict__ y, const E* __restrict__ v, double eps, int64_t P, E* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < P) out[i] = rscale(eps, v[i]) + mk<E>(y[i].re, y[i].im);
+}
+
+template <typename E>
+struct CgOps {
+    nq_ctx_t ctx;
+    int64_t P;
+    // explicit
+    const E* S = nullptr;
+    double eps = 0.0;
+    // matrix-free
+    const void* O = nullptr; int64_t ld = 0, Ns = 0, Ns_total = 0; nq_dtype odtype = NQ_C128;
+    int matvec(const E* v, E* out) {
+        if (S) {
+            int nslice = (int)std::max<int64_t>(1, std::min<int64_t>(64, P / 64));
+            E* partial = (E*)nq_scratch(ctx, SL_W4, (size_t)nslice * P * sizeof(E));
+            if (!partial) return NQ_ERR_ALLOC;
+            dim3 grid((unsigned)((P + 127) / 128), (unsigned)nslice);
+            NQ_LAUNCH(ctx, gemv_partial_kernel<E>, grid, 128, 0, S, P, v, partial);
+            NQ_LAUNCH(ctx, gemv_final_kernel<E>, (unsigned)((P + 255) / 256), 256, 0, (const E*)partial, nslice, P, v, eps, out);
+            return NQ_OK;
+        }
+        // t = O^T v (complex, precision of O), y = sum_s conj(O[:,s]) t[s] / Ns_total, out = eps v + y
+        size_t tb = (size_t)Ns * nq_dtype_size(nq_complex_of(odtype));
+        void* t = nq_scratch(ctx, SL_W3, tb ? tb : 16);
+        cxd* y = (cxd*)nq_scratch(ctx, SL_W4, (size_t)P * sizeof(cxd));
+        if (!t || !y) return NQ_ERR_ALLOC;
+        unsigned g = (unsigned)((Ns * 32 + 255) / 256);
+        switch (odtype) {
+            case NQ_F32: NQ_LAUNCH(ctx, (ot_v_kernel<float, E>), g, 256, 0, (const float*)O, ld, P, Ns, v, (cxf*)t); break;
+            case NQ_F64: NQ_LAUNCH(ctx, (ot_v_kernel<double, E>), g, 256, 0, (const double*)O, ld, P, Ns, v, (cxd*)t); break;
+            case NQ_C64: NQ_LAUNCH(ctx, (ot_v_kernel<cxf, E>), g, 256, 0, (const cxf*)O, ld, P, Ns, v, (cxf*)t); break;
+            default: NQ_LAUNCH(ctx, (ot_v_kernel<cxd, E>), g, 256, 0, (const cxd*)O, ld, P, Ns, v, (cxd*)t); break;
+        }
+        NQ_CHECK(colsum_dispatch<true>(ctx, odtype, O, ld, P, Ns, t, 1.0 / (double)Ns_total, y));
+        if (ctx->nccl_comm) NQ_CHECK(nq_allreduce_device(ctx, y, P, NQ_C128, false));
+        NQ_LAUNCH(ctx, matfree_finish_kernel<E>, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)y, v, eps, P, out);
+        return NQ_OK;
+    }
+};
+
+// IterativeSolvers 0.8.1 cg: x0 = 0, u = 0, r = b; converged when ||r|| <= tol ||b||
+template <typename E>
+int cg_solve(CgOps<E>& ops, const E* b, double tol, int64_t maxiter, E* x, int64_t* iters) {
+    nq_ctx_t ctx = ops.ctx;
+    const int64_t P = ops.P;
+    E* work = (E*)nq_scratch(ctx, SL_W2, (size_t)3 * P * sizeof(E) + 64);
+    if (!work) return NQ_ERR_ALLOC;
+    E *u = work, *r = work + P, *c = work + 2 * P;
+    double* dsc = (double*)nq_scratch(ctx, SL_W1, 64);
+    if (!dsc) return NQ_ERR_ALLOC;
+    unsigned gv = (unsigned)((P + 255) / 256);
+    NQ_CUDA(ctx, cudaMemsetAsync(x, 0, (size_t)P * sizeof(E), ctx->stream));
+    NQ_CUDA(ctx, cudaMemsetAsync(u, 0, (size_t)P * sizeof(E), ctx->stream));
+    NQ_CUDA(ctx, cudaMemcpyAsync(r, b, (size_t)P * sizeof(E), cudaMemcpyDeviceToDevice, ctx->stream));
+    double h[2];
+    NQ_LAUNCH(ctx, dot_kernel<E>, 1, 1024, 0, (const E*)r, (const E*)r, P, dsc);
+    NQ_CUDA(ctx, cudaMemcpyAsync(h, dsc, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double residual = sqrt(h[0]), prev = 1.0;
+    const double reltol = residual * tol;
+    int64_t it = 0;
+    while (it < maxiter && !(residual <= reltol)) {
+        double beta = residual * residual / (prev * prev);
+        NQ_LAUNCH(ctx, cg_update_u_kernel<E>, gv, 256, 0, u, (const E*)r, beta, P);
+        NQ_CHECK(ops.matvec(u, c));
+        NQ_LAUNCH(ctx, dot_kernel<E>, 1, 1024, 0, (const E*)u, (const E*)c, P, dsc);
+        NQ_LAUNCH(ctx, cg_update_xr_kernel<E>, gv, 256, 0, x, r, (const E*)u, (const E*)c, residual * residual, (const double*)dsc, P);
+        NQ_LAUNCH(ctx, dot_kernel<E>, 1, 1024, 0, (const E*)r, (const E*)r, P, dsc + 2);
+        NQ_CUDA(ctx, cudaMemcpyAsync(h, dsc + 2, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        prev = residual;
+        residual = sqrt(h[0]);
+        it++;
+    }
+    if (iters) *iters = it;
+    return residual <= reltol ? NQ_OK : NQ_ERR_NOT_CONVERGED;
+}
+
+template <typename E>
+__global__ void update_kernel(E* __restrict__ w, const E* __restrict__ dw, typename elem_traits<E>::real eta, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) w[i] = w[i] - rscale(eta, dw[i]);
+}
+
+// per-chain mean and centred second moment of vals[B, L] (column-major: chain fastest)
+template <typename E>
+__global__ void chain_stats_kernel(const E* __restrict__ vals, int64_t B, int64_t L, double* __restrict__ out /* [B][3] */) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double mr = 0.0, mi = 0.0;
+    for (int64_t l = 0; l < L; l++) { mr += (double)real_part(vals[b + B * l]); mi += (double)imag_part(vals[b + B * l]); }
+    mr /= (double)L; mi /= (double)L;
+    double m2 = 0.0;
+    for (int64_t l = 0; l < L; l++) {
+        double dr = (double)real_part(vals[b + B * l]) - mr, di = (double)imag_part(vals[b + B * l]) - mi;
+        m2 += dr * dr + di * di;
+    }
+    out[3 * b] = mr; out[3 * b + 1] = mi; out[3 * b + 2] = m2;
+}
+
+template <typename T>
+__global__ void abs2_kernel(const cx<T>* __restrict__ in, T* __restrict__ out, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i].re * in[i].re + in[i].im * in[i].im;
+}
+
+}  // namespace
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+extern "C" int nq_abs2(nq_ctx_t ctx, const void* vals, int64_t n, nq_dtype vdtype, void* out) {
+    if (!ctx || !vals || !out || n < 0) return NQ_ERR_ARG;
+    if (!nq_dtype_is_complex(vdtype)) return nq_fail(ctx, NQ_ERR_ARG, "nq_abs2 takes complex values");
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    NqStage st(ctx);
+    const void* dv = st.in(SL_IN0, vals, (size_t)n * nq_dtype_size(vdtype));
+    void* dout = st.out(SL_OUT0, out, (size_t)n * nq_dtype_size(nq_real_of(vdtype)));
+    if (st.status != NQ_OK) return st.status;
+    if (n > 0) {
+        unsigned g = (unsigned)((n + 255) / 256);
+        if (vdtype == NQ_C64) NQ_LAUNCH(ctx, abs2_kernel<float>, g, 256, 0, (const cxf*)dv, (float*)dout, n);
+        else NQ_LAUNCH(ctx, abs2_kernel<double>, g, 256, 0, (const cxd*)dv, (double*)dout, n);
+    }
+    return st.finish();
+}
+
+extern "C" int nq_center(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype, void* avg) {
+    if (!ctx || !O || !avg || P <= 0 || Ns <= 0 || ldO < P) return NQ_ERR_ARG;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!nq_is_device_ptr(O)) return nq_fail(ctx, NQ_ERR_ARG, "nq_center works in place on a device-resident O");
+    NqStage st(ctx);
+    void* davg = st.out(SL_OUT0, avg, (size_t)P * nq_dtype_size(dtype));
+    cxd* a = (cxd*)nq_scratch(ctx, SL_W0, (size_t)P * sizeof(cxd));
+    if (!a || st.status != NQ_OK) return NQ_ERR_ALLOC;
+    NQ_CHECK(colsum_dispatch<false>(ctx, dtype, O, ldO, P, Ns, nullptr, 1.0, a));
+    // under sharding: <O> is the global mean (C1, BaseIterativeSampler.jl:23)
+    if (ctx->nccl_comm) {
+        NQ_CHECK(nq_allreduce_device(ctx, a, P, NQ_C128, false));
+    }
+    // a currently holds the (global) sum; divide by the global sample count
+    {
+        int64_t ns_tot = Ns * ctx->nranks;
+        cxd* tmp = (cxd*)nq_scratch(ctx, SL_W1, (size_t)P * sizeof(cxd));
+        if (!tmp) return NQ_ERR_ALLOC;
+        NQ_LAUNCH(ctx, colsum_final_kernel<double>, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)a, 1, P, 1.0 / (double)ns_tot, tmp);
+        a = tmp;
+    }
+    dim3 grid((unsigned)((P + 127) / 128), (unsigned)std::min<int64_t>(Ns, 4096));
+    switch (dtype) {
+        case NQ_F32: NQ_LAUNCH(ctx, subtract_avg_kernel<float>, grid, 128, 0, (float*)O, ldO, P, Ns, (const cxd*)a); break;
+        case NQ_F64: NQ_LAUNCH(ctx, subtract_avg_kernel<double>, grid, 128, 0, (double*)O, ldO, P, Ns, (const cxd*)a); break;
+        case NQ_C64: NQ_LAUNCH(ctx, subtract_avg_kernel<cxf>, grid, 128, 0, (cxf*)O, ldO, P, Ns, (const cxd*)a); break;
+        default: NQ_LAUNCH(ctx, subtract_avg_kernel<cxd>, grid, 128, 0, (cxd*)O, ldO, P, Ns, (const cxd*)a); break;
+    }
+    NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)a, davg, P, (int)dtype, 0);
+    return st.finish();
+}
+
+extern "C" int nq_force_ket(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype,
+                            const void* Eloc, void* gradC) {
+    if (!ctx || !Oc || !Eloc || !gradC || P <= 0 || Ns <= 0 || ldO < P) return NQ_ERR_ARG;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!nq_is_device_ptr(Oc)) return nq_fail(ctx, NQ_ERR_ARG, "Oc must be device-resident");
+    NqStage st(ctx);
+    nq_dtype cdt = nq_complex_of(dtype);
+    const void* dE = st.in(SL_IN0, Eloc, (size_t)Ns * nq_dtype_size(cdt));
+    void* dg = st.out(SL_OUT0, gradC, (size_t)P * nq_dtype_size(cdt));
+    cxd* a = (cxd*)nq_scratch(ctx, SL_W0, (size_t)P * sizeof(cxd));
+    if (!a || st.status != NQ_OK) return NQ_ERR_ALLOC;
+    int64_t ns_tot = Ns * ctx->nranks;
+    NQ_CHECK(colsum_dispatch<true>(ctx, dtype, Oc, ldO, P, Ns, dE, 1.0 / (double)ns_tot, a));
+    if (ctx->nccl_comm) NQ_CHECK(nq_allreduce_device(ctx, a, P, NQ_C128, false));   // C3
+    NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)a, dg, P, (int)cdt, 0);
+    return st.finish();
+}
+
+extern "C" int nq_force_liouvillian(nq_ctx_t ctx, const void* Lloc, const void* gLloc, int64_t ld, int64_t P, int64_t Ns,
+                                    nq_dtype dtype, const void* avg, void* gradC, double* cost) {
+    if (!ctx || !Lloc || !gLloc || !avg || !gradC || P <= 0 || Ns <= 0 || ld < P) return NQ_ERR_ARG;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!nq_is_device_ptr(gLloc)) return nq_fail(ctx, NQ_ERR_ARG, "grad L_loc must be device-resident");
+    if (!nq_dtype_is_complex(dtype)) return nq_fail(ctx, NQ_ERR_ARG, "L_loc / grad L_loc are complex");
+    NqStage st(ctx);
+    size_t cs = nq_dtype_size(dtype);
+    const void* dL = st.in(SL_IN0, Lloc, (size_t)Ns * cs);
+    const void* davg = st.in(SL_IN1, avg, (size_t)P * cs);
+    void* dg = st.out(SL_OUT0, gradC, (size_t)P * cs);
+    if (st.status != NQ_OK) return st.status;
+    // packed reduction buffer: [ sum_s L_s conj(gL_ks) (P complex) | sum_s |L_s|^2 ]  -> one all-reduce
+    cxd* a = (cxd*)nq_scratch(ctx, SL_W0, (size_t)(P + 1) * sizeof(cxd));
+    cxd* avgd = (cxd*)nq_scratch(ctx, SL_W1, (size_t)P * sizeof(cxd));
+    cxd* outd = (cxd*)nq_scratch(ctx, SL_W2, (size_t)P * sizeof(cxd));
+    if (!a || !avgd || !outd) return NQ_ERR_ALLOC;
+    int64_t ns_tot = Ns * ctx->nranks;
+    // (1/Ns) sum_s L_s conj(gL_ks), conjugated at the end: F_k = conj(.) - C avg_k
+    NQ_CHECK(colsum_dispatch<true>(ctx, dtype, gLloc, ld, P, Ns, dL, 1.0 / (double)ns_tot, a));
+    NQ_CUDA(ctx, cudaMemsetAsync(a + P, 0, sizeof(cxd), ctx->stream));
+    if (dtype == NQ_C64) NQ_LAUNCH(ctx, abs2_sum_kernel<float>, 1, 1024, 0, (const cxf*)dL, Ns, (double*)(a + P));
+    else NQ_LAUNCH(ctx, abs2_sum_kernel<double>, 1, 1024, 0, (const cxd*)dL, Ns, (double*)(a + P));
+    if (ctx->nccl_comm) NQ_CHECK(nq_allreduce_device(ctx, a, P + 1, NQ_C128, false));   // C2 + C3 packed
+    NQ_LAUNCH(ctx, convert_to_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, davg, avgd, P, (int)dtype);
+    // conj of the column sum, then subtract C avg
+    cxd* lg = (cxd*)nq_scratch(ctx, SL_W3, (size_t)P * sizeof(cxd));
+    if (!lg) return NQ_ERR_ALLOC;
+    NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)a, (void*)lg, P, (int)NQ_C128, 1);
+    NQ_LAUNCH(ctx, force_liouv_finish_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)lg, (const cxd*)avgd,
+              (const double*)(a + P), 1.0 / (double)ns_tot, P, outd);
+    NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)outd, dg, P, (int)dtype, 0);
+    if (cost) {
+        double s = 0.0;
+        NQ_CUDA(ctx, cudaMemcpyAsync(&s, a + P, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *cost = s / (double)ns_tot;
+    }
+    return st.finish();
+}
+
+extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total,
+                           nq_dtype dtype, const void* gradC, int real_params, void* S, void* F) {
+    if (!ctx || !Oc || !gradC || !S || !F || P <= 0 || Ns <= 0 || ldO < P || Ns_total < Ns) return NQ_ERR_ARG;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!nq_is_device_ptr(Oc)) return nq_fail(ctx, NQ_ERR_ARG, "Oc must be device-resident");
+    const bool ocx = nq_dtype_is_complex(dtype);
+    const bool out_complex = ocx && !real_params;
+    // S/F dtype: real nets -> real of the same precision; complex nets -> complex
+    nq_dtype sdt = out_complex ? dtype : nq_real_of(dtype);
+    NqStage st(ctx);
+    nq_dtype cdt = nq_complex_of(dtype);
+    const void* dgc = st.in(SL_IN0, gradC, (size_t)P * nq_dtype_size(cdt));
+    void* dS = st.out(SL_OUT0, S, (size_t)P * P * nq_dtype_size(sdt));
+    void* dF = st.out(SL_OUT1, F, (size_t)P * nq_dtype_size(sdt));
+    if (st.status != NQ_OK) return st.status;
+    const int ntile = (int)((P + TS - 1) / TS);
+    const int64_t Ppad = (int64_t)ntile * TS;
+    const int64_t ntri = (int64_t)ntile * (ntile + 1) / 2;
+    int nsplit = (int)std::max<int64_t>(1, (4 * (int64_t)ctx->num_sms + ntri - 1) / ntri);
+    nsplit = (int)std::min<int64_t>(nsplit, std::max<int64_t>(1, Ns / (8 * KS)));
+    const size_t plane = (size_t)Ppad * Ppad * sizeof(double);
+    while (nsplit > 1 && plane * nsplit * (out_complex ? 2 : 1) > ((size_t)2 << 30)) nsplit--;
+    double* Wre = (double*)nq_scratch(ctx, SL_W0, plane * nsplit);
+    double* Wim = out_complex ? (double*)nq_scratch(ctx, SL_W1, plane * nsplit) : nullptr;
+    if (!Wre || (out_complex && !Wim)) return NQ_ERR_ALLOC;
+    const int64_t ldr = ldO * (ocx ? 2 : 1);
+    if (ocx) {
+        if (nq_dtype_is_double(dtype)) {
+            NQ_CHECK((launch_syrk<double, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
+            if (out_complex) NQ_CHECK((launch_syrk<double, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 1, Wim)));
+        } else {
+            NQ_CHECK((launch_syrk<float, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
+            if (out_complex) NQ_CHECK((launch_syrk<float, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 1, Wim)));
+        }
+    } else {
+        if (nq_dtype_is_double(dtype)) NQ_CHECK((launch_syrk<double, 1>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
+        else NQ_CHECK((launch_syrk<float, 1>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
+    }
+    dim3 grid((unsigned)((P + 127) / 128), (unsigned)P);
+    const double scale = 1.0 / (double)Ns_total;
+    if (nq_dtype_is_double(dtype))
+        NQ_LAUNCH(ctx, syrk_finalize_kernel<double>, grid, 128, 0, (const double*)Wre, (const double*)Wim, nsplit, Ppad, P, scale, (int)out_complex, (double*)dS);
+    else
+        NQ_LAUNCH(ctx, syrk_finalize_kernel<float>, grid, 128, 0, (const double*)Wre, (const double*)Wim, nsplit, Ppad, P, scale, (int)out_complex, (float*)dS);
+    // F = gradC (complex nets) or Re(gradC)
+    cxd* tmp = (cxd*)nq_scratch(ctx, SL_W2, (size_t)P * sizeof(cxd));
+    if (!tmp) return NQ_ERR_ALLOC;
+    NQ_LAUNCH(ctx, convert_to_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, dgc, tmp, P, (int)cdt);
+    NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)tmp, dF, P, (int)sdt, 0);
+    return st.finish();
+}
+
+template <typename E>
+static int solve_typed(nq_ctx_t ctx, const cxd* Sd, const cxd* Fd, int64_t P, double eps, nq_solver algo, double tol,
+                       int64_t maxiter, cxd* xd, int64_t* iters);
+
+// convert (possibly complex) cxd arrays to E arrays and back
+__global__ void cxd_to_real_kernel(const cxd* __restrict__ in, double* __restrict__ out, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i].re;
+}
+
+extern "C" int nq_sr_solve(nq_ctx_t ctx, void* S, const void* F, int64_t P, nq_dtype sdtype, double eps, nq_solver algo,
+                           double tol, int64_t maxiter, void* dw, int64_t* iters) {
+    if (!ctx || !S || !F || !dw || P <= 0) return NQ_ERR_ARG;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    NqStage st(ctx);
+    const size_t es = nq_dtype_size(sdtype);
+    const void* dS = st.in(SL_IN0, S, (size_t)P * P * es);
+    const void* dF = st.in(SL_IN1, F, (size_t)P * es);
+    void* ddw = st.out(SL_OUT0, dw, (size_t)P * es);
+    if (st.status != NQ_OK) return st.status;
+    const bool cplx = nq_dtype_is_complex(sdtype);
+    const size_t ws = cplx ? sizeof(cxd) : sizeof(double);
+    // double-precision working copies (S itself if it already is double and on the device)
+    void* A = nullptr;
+    nq_dtype wdt = cplx ? NQ_C128 : NQ_F64;
+    const int64_t nn = P * P;
+    if (sdtype == wdt && nq_is_device_ptr(S)) A = S;
+    else {
+        A = nq_scratch(ctx, SL_W0, (size_t)nn * ws);
+        if (!A) return NQ_ERR_ALLOC;
+        if (sdtype == wdt) NQ_CUDA(ctx, cudaMemcpyAsync(A, dS, (size_t)nn * ws, cudaMemcpyDeviceToDevice, ctx->stream));
+        else if (cplx) NQ_LAUNCH(ctx, convert_to_cxd_kernel, (unsigned)((nn + 255) / 256), 256, 0, dS, (cxd*)A, nn, (int)sdtype);
+        else {
+            cxd* t = (cxd*)nq_scratch(ctx, SL_W5, (size_t)nn * sizeof(cxd));
+            if (!t) return NQ_ERR_ALLOC;
+            NQ_LAUNCH(ctx, convert_to_cxd_kernel, (unsigned)((nn + 255) / 256), 256, 0, dS, t, nn, (int)sdtype);
+            NQ_LAUNCH(ctx, cxd_to_real_kernel, (unsigned)((nn + 255) / 256), 256, 0, (const cxd*)t, (double*)A, nn);
+        }
+    }
+    void* b = nq_scratch(ctx, SL_W3, (size_t)2 * P * ws);
+    if (!b) return NQ_ERR_ALLOC;
+    void* x = (char*)b + (size_t)P * ws;
+    {
+        cxd* t = (cxd*)nq_scratch(ctx, SL_W4, (size_t)P * sizeof(cxd));
+        if (!t) return NQ_ERR_ALLOC;
+        NQ_LAUNCH(ctx, convert_to_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, dF, t, P, (int)sdtype);
+        NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)t, b, P, (int)wdt, 0);
+    }
+    int status = NQ_OK;
+    int64_t its = 0;
+    if (algo == NQ_SOLVE_CHOLESKY) {
+        int* dinfo = (int*)nq_scratch(ctx, SL_W1, 16);
+        if (!dinfo) return NQ_ERR_ALLOC;
+        NQ_CUDA(ctx, cudaMemsetAsync(dinfo, 0xff, 4, ctx->stream));
+        NQ_CUDA(ctx, cudaMemcpyAsync(x, b, (size_t)P * ws, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (cplx) {
+            NQ_LAUNCH(ctx, add_diag_kernel<cxd>, (unsigned)((P + 255) / 256), 256, 0, (cxd*)A, P, eps);
+            NQ_CHECK(cholesky_solve<cxd>(ctx, (cxd*)A, P, (cxd*)x, dinfo));
+        } else {
+            NQ_LAUNCH(ctx, add_diag_kernel<double>, (unsigned)((P + 255) / 256), 256, 0, (double*)A, P, eps);
+            NQ_CHECK(cholesky_solve<double>(ctx, (double*)A, P, (double*)x, dinfo));
+        }
+        int hinfo = -1;
+        NQ_CUDA(ctx, cudaMemcpyAsync(&hinfo, dinfo, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (hinfo >= 0) {
+            ctx->info = hinfo;
+            status = nq_fail(ctx, NQ_ERR_NOT_POSDEF, "Cholesky: non-positive pivot at index %d", hinfo);
+        }
+    } else if (algo == NQ_SOLVE_CG) {
+        if (maxiter <= 0) maxiter = 10 * P;
+        if (cplx) {
+            CgOps<cxd> ops; ops.ctx = ctx; ops.P = P; ops.S = (const cxd*)A; ops.eps = eps;
+            status = cg_solve<cxd>(ops, (const cxd*)b, tol, maxiter, (cxd*)x, &its);
+        } else {
+            CgOps<double> ops; ops.ctx = ctx; ops.P = P; ops.S = (const double*)A; ops.eps = eps;
+            status = cg_solve<double>(ops, (const double*)b, tol, maxiter, (double*)x, &its);
+        }
+        if (status != NQ_OK && status != NQ_ERR_NOT_CONVERGED) return status;
+        if (status == NQ_ERR_NOT_CONVERGED) nq_fail(ctx, status, "CG: not converged after %lld iterations", (long long)its);
+    } else return nq_fail(ctx, NQ_ERR_ARG, "unknown solver");
+    if (iters) *iters = its;
+    {
+        cxd* t = (cxd*)nq_scratch(ctx, SL_W4, (size_t)P * sizeof(cxd));
+        NQ_LAUNCH(ctx, convert_to_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const void*)x, t, P, (int)wdt);
+        NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)t, ddw, P, (int)sdtype, 0);
+    }
+    int fs = st.finish();
+    return fs != NQ_OK ? fs : status;
+}
+
+extern "C" int nq_sr_solve_matfree(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total,
+                                   nq_dtype dtype, const void* F, int real_params, double eps, double tol, int64_t maxiter,
+                                   void* dw, int64_t* iters) {
+    if (!ctx || !Oc || !F || !dw || P <= 0 || Ns <= 0 || ldO < P || Ns_total < Ns) return NQ_ERR_ARG;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!nq_is_device_ptr(Oc)) return nq_fail(ctx, NQ_ERR_ARG, "Oc must be device-resident");
+    const bool out_complex = nq_dtype_is_complex(dtype) && !real_params;
+    nq_dtype sdt = out_complex ? dtype : nq_real_of(dtype);
+    nq_dtype wdt = out_complex ? NQ_C128 : NQ_F64;
+    const size_t ws = nq_dtype_size(wdt);
+    NqStage st(ctx);
+    const void* dF = st.in(SL_IN0, F, (size_t)P * nq_dtype_size(sdt));
+    void* ddw = st.out(SL_OUT0, dw, (size_t)P * nq_dtype_size(sdt));
+    if (st.status != NQ_OK) return st.status;
+    void* b = nq_scratch(ctx, SL_W0, (size_t)2 * P * ws);
+    cxd* t = (cxd*)nq_scratch(ctx, SL_IN4, (size_t)P * sizeof(cxd));
+    if (!b || !t) return NQ_ERR_ALLOC;
+    void* x = (char*)b + (size_t)P * ws;
+    NQ_LAUNCH(ctx, convert_to_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, dF, t, P, (int)sdt);
+    NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)t, b, P, (int)wdt, 0);
+    if (maxiter <= 0) maxiter = 10 * P;
+    int status;
+    int64_t its = 0;
+    if (out_complex) {
+        CgOps<cxd> ops; ops.ctx = ctx; ops.P = P; ops.eps = eps; ops.O = Oc; ops.ld = ldO; ops.Ns = Ns; ops.Ns_total = Ns_total; ops.odtype = dtype;
+        status = cg_solve<cxd>(ops, (const cxd*)b, tol, maxiter, (cxd*)x, &its);
+    } else {
+        CgOps<double> ops; ops.ctx = ctx; ops.P = P; ops.eps = eps; ops.O = Oc; ops.ld = ldO; ops.Ns = Ns; ops.Ns_total = Ns_total; ops.odtype = dtype;
+        status = cg_solve<double>(ops, (const double*)b, tol, maxiter, (double*)x, &its);
+    }
+    if (status != NQ_OK && status != NQ_ERR_NOT_CONVERGED) return status;
+    if (status == NQ_ERR_NOT_CONVERGED) nq_fail(ctx, status, "CG: not converged after %lld iterations", (long long)its);
+    if (iters) *iters = its;
+    NQ_LAUNCH(ctx, convert_to_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const void*)x, t, P, (int)wdt);
+    NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)t, ddw, P, (int)sdt, 0);
+    int fs = st.finish();
+    return fs != NQ_OK ? fs : status;
+}
+
+extern "C" int nq_update(nq_machine_t m, const void* dw, double eta) {
+    if (!m || !dw) return NQ_ERR_ARG;
+    nq_ctx_t ctx = m->ctx;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    NqStage st(ctx);
+    const void* d = st.in(SL_IN0, dw, (size_t)m->P * nq_dtype_size(m->dtype));
+    if (st.status != NQ_OK) return st.status;
+    unsigned g = (unsigned)((m->P + 255) / 256);
+    switch (m->dtype) {
+        case NQ_F32: NQ_LAUNCH(ctx, update_kernel<float>, g, 256, 0, (float*)m->params, (const float*)d, (float)eta, m->P); break;
+        case NQ_F64: NQ_LAUNCH(ctx, update_kernel<double>, g, 256, 0, (double*)m->params, (const double*)d, eta, m->P); break;
+        case NQ_C64: NQ_LAUNCH(ctx, update_kernel<cxf>, g, 256, 0, (cxf*)m->params, (const cxf*)d, (float)eta, m->P); break;
+        default: NQ_LAUNCH(ctx, update_kernel<cxd>, g, 256, 0, (cxd*)m->params, (const cxd*)d, eta, m->P); break;
+    }
+    if (!nq_is_device_ptr(dw)) NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NQ_OK;
+}
+
+extern "C" int nq_stat_analysis(nq_ctx_t ctx, const void* vals, int64_t B, int64_t L, nq_dtype vdtype, double out[6]) {
+    if (!ctx || !vals || !out || B <= 0 || L <= 0) return NQ_ERR_ARG;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    NqStage st(ctx);
+    const void* dv = st.in(SL_IN0, vals, (size_t)B * L * nq_dtype_size(vdtype));
+    double* dst = (double*)nq_scratch(ctx, SL_W0, (size_t)B * 3 * sizeof(double));
+    if (st.status != NQ_OK || !dst) return NQ_ERR_ALLOC;
+    unsigned g = (unsigned)((B + 127) / 128);
+    switch (vdtype) {
+        case NQ_F32: NQ_LAUNCH(ctx, chain_stats_kernel<float>, g, 128, 0, (const float*)dv, B, L, dst); break;
+        case NQ_F64: NQ_LAUNCH(ctx, chain_stats_kernel<double>, g, 128, 0, (const double*)dv, B, L, dst); break;
+        case NQ_C64: NQ_LAUNCH(ctx, chain_stats_kernel<cxf>, g, 128, 0, (const cxf*)dv, B, L, dst); break;
+        default: NQ_LAUNCH(ctx, chain_stats_kernel<cxd>, g, 128, 0, (const cxd*)dv, B, L, dst); break;
+    }
+    std::vector<double> h((size_t)B * 3);
+    NQ_CUDA(ctx, cudaMemcpyAsync(h.data(), dst, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // combine the per-chain moments exactly as utils/stats.jl:26-50 defines them
+    double mr = 0, mi = 0, m2sum = 0;
+    for (int64_t b = 0; b < B; b++) { mr += h[3 * b]; mi += h[3 * b + 1]; m2sum += h[3 * b + 2]; }
+    mr /= B; mi /= B;
+    double between = 0;
+    for (int64_t b = 0; b < B; b++) { double dr = h[3 * b] - mr, di = h[3 * b + 1] - mi; between += dr * dr + di * di; }
+    double var_chains_mean = L > 1 ? (m2sum / (double)(L - 1)) / (double)B : NAN;
+    double var_mu_ch = B > 1 ? between / (double)(B - 1) : NAN;
+    double var_mu = (B * L > 1) ? (m2sum + (double)L * between) / (double)(B * L - 1) : NAN;
+    double t = var_mu_ch / var_mu;
+    out[0] = mr; out[1] = mi;
+    out[2] = sqrt(var_mu_ch / (double)B);
+    out[3] = var_chains_mean;
+    out[4] = std::max(0.0, 0.5 * (t * (double)L - 1.0));
+    out[5] = sqrt((double)(L - 1) / (double)L + t);
+    return NQ_OK;
+}

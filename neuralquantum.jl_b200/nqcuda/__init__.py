@@ -1,0 +1,19 @@
+"""nqcuda -- host-side mirror of NeuralQuantum.jl's machine / sampler / operator / algorithm /
+parallel interfaces over libnqcuda (hand-written CUDA for sm_100a).  Importing this package loads
+the shared library and fails loudly if it is missing: there is no CPU fallback.
+"""
+from . import _lib
+from ._lib import NQError, PosDefException, NotConvergedError, EXPORTS, LIB_PATH
+from .core import Context, HomogeneousSpin, HomogeneousFock, Hilbert, unique_id
+from .operators import (LocalOperator as _LocalOperator, KLocalOperatorRow, Liouvillian, liouvillian, sigmax, sigmay,
+                        sigmaz, sigmam, sigmap, destroy, create, number, DeviceOperator)
+from .machines import RBM, RBMSplit, NDM, af_softplus, af_logcosh, init_random_pars_
+from .samplers import MetropolisSampler, MetropolisSamplerCache, LocalRule
+from .algorithms import (SR, Descent, update_, local_scalar, local_grad, stat_analysis, Measurement, sr_cholesky,
+                         sr_cg)
+from .iterative import BatchedSampler
+
+
+def LocalOperator(hilb):
+    """LocalOperator(hilb): the zero operator on `hilb` (KLocalZero.jl)."""
+    return _LocalOperator(hilb)

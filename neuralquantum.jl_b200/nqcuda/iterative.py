@@ -1,0 +1,179 @@
+"""BatchedSampler: the per-iteration driver (sample! -> precondition! -> update!) with every
+buffer resident on the GPU; PyTorch is used only to own device memory.
+
+ref: src/IterativeInterface/build_Batched.jl:1-14, Samplers/CostFun/BatchedValSampler.jl:117-139,
+     Samplers/CostFun/BatchedGradSampler.jl:77-123, Samplers/BaseIterativeSampler.jl:5-26,
+     src/Algorithms/SR/SRDirect.jl, SRIterative.jl.
+Differences kept on purpose: all L slices of the chain are filled (Q3), S is
+normalised by the global sample count under sharding (Q5), statistics are global (Q15).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .algorithms import Measurement, SR, sr_cg, sr_cholesky, stat_analysis
+from .operators import Liouvillian
+from .samplers import MetropolisSamplerCache
+
+
+def _torch():
+    import torch
+    return torch
+
+
+_TORCH_OF = None
+
+
+def _tdtype(np_dtype):
+    torch = _torch()
+    return {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+            np.dtype(np.complex64): torch.complex64, np.dtype(np.complex128): torch.complex128}[np.dtype(np_dtype)]
+
+
+class BatchedSampler:
+    """BatchedSampler(net, sampler, problem, algo; batch_sz).  `problem` is a LocalOperator (ground
+    state, BatchedValSampler) or a Liouvillian (steady state, BatchedGradSampler)."""
+
+    def __init__(self, net, sampler, problem, algo=None, batch_sz=16, chain_length=None):
+        torch = _torch()
+        self.net, self.sampler, self.problem = net, sampler, problem
+        self.algo = algo if algo is not None else SR()
+        self.ctx = ctx = net.ctx
+        self.is_liouvillian = isinstance(problem, Liouvillian)
+        if self.is_liouvillian != net.doubled:
+            raise ValueError("ket machines pair with Hamiltonians, density-matrix machines with Liouvillians")
+        self.op = problem.to_device(ctx)
+        self.nranks, self.rank = ctx.comm_size()
+        self.B = int(batch_sz)
+        self.cache = MetropolisSamplerCache(sampler, net, self.B, chain_offset=self.rank * self.B,
+                                            num_workers=self.nranks)
+        self.L = self.cache.loc_chain_length if chain_length is None else int(chain_length)
+        self.Ns = self.B * self.L
+        self.Ns_total = self.Ns * self.nranks
+        dev = torch.device("cuda", ctx.device)
+        W = L.lib.nq_states_words(net.N)
+        P, Ns = net.P, self.Ns
+        ot, ct = _tdtype(net.out_dtype), _tdtype(net.cdtype)
+        self.prow = torch.zeros((self.L, self.B, W), dtype=torch.int64, device=dev)
+        self.pcol = torch.zeros_like(self.prow) if net.doubled else None
+        self.logpsi = torch.zeros(Ns, dtype=ot, device=dev)
+        self.O = torch.zeros((Ns, P), dtype=ot, device=dev)            # = [P, Ns] column-major
+        self.loc = torch.zeros(Ns, dtype=ct, device=dev)
+        self.gloc = torch.zeros((Ns, P), dtype=ct, device=dev) if self.is_liouvillian else None
+        self.avg = torch.zeros(P, dtype=ot, device=dev)
+        self.gradC = torch.zeros(P, dtype=ct, device=dev)
+        self.real_params = net.real_params
+        st = _tdtype(net.rdtype) if self.real_params else ct
+        self.sdtype = np.dtype(net.rdtype) if self.real_params else np.dtype(net.cdtype)
+        explicit = self.algo.algorithm == sr_cholesky or self.algo.full_matrix
+        self.S = torch.zeros((P, P), dtype=st, device=dev) if explicit else None
+        self.F = torch.zeros(P, dtype=st, device=dev)
+        self.dw = torch.zeros(P, dtype=st, device=dev)
+        self.abs2 = torch.zeros(Ns, dtype=_tdtype(net.rdtype), device=dev) if self.is_liouvillian else None
+        self.cost = None
+        self.last_iters = 0
+
+    # ---- the hot path -----------------------------------------------------------------
+    def sample_states(self):
+        """_sample_state!: re-randomise the chains, burn, fill the L slices."""
+        self.cache.randomize()
+        self.cache.sample(self.sampler.burn_length, self.L,
+                          packed_out=(self.prow.data_ptr(), self.pcol.data_ptr() if self.pcol is not None else None))
+
+    def set_samples(self, sigma):
+        """Bypass the sampler with supplied configurations [N, B, L] (parity tests / benchmarks)."""
+        net, ctx = self.net, self.ctx
+        sr, sc = sigma if net.doubled else (sigma, None)
+        for arr, buf in ((sr, self.prow), (sc, self.pcol)):
+            if arr is None:
+                continue
+            a = np.asfortranarray(arr).reshape(net.N, self.Ns, order="F")
+            L.check(L.lib.nq_pack_states(ctx.h, net.hilb.code, net.N, self.Ns, L.ptr(a), L.nq_dtype(a.dtype),
+                                         buf.data_ptr()), ctx.h)
+
+    def evaluate(self):
+        """logpsi_and_grad! + local estimator on the stored samples."""
+        net, ctx, Ns = self.net, self.ctx, self.Ns
+        pc = self.pcol.data_ptr() if self.pcol is not None else None
+        L.check(L.lib.nq_logpsi_grad_packed(net.h, self.prow.data_ptr(), pc, Ns, self.logpsi.data_ptr(),
+                                            self.O.data_ptr(), net.P), ctx.h)
+        if self.is_liouvillian:
+            L.check(L.lib.nq_local_grad_packed(net.h, self.op.h, self.prow.data_ptr(), pc, Ns, self.loc.data_ptr(),
+                                               self.gloc.data_ptr(), net.P), ctx.h)
+        else:
+            L.check(L.lib.nq_local_scalar_packed(net.h, self.op.h, self.prow.data_ptr(), pc, Ns, self.loc.data_ptr()),
+                    ctx.h)
+
+    def assemble(self):
+        """centre O, force vector, SR setup (S, F)."""
+        net, ctx, Ns, P = self.net, self.ctx, self.Ns, self.net.P
+        oc = L.nq_dtype(net.out_dtype)
+        cc = L.nq_dtype(net.cdtype)
+        L.check(L.lib.nq_center(ctx.h, self.O.data_ptr(), P, P, Ns, oc, self.avg.data_ptr()), ctx.h)
+        if self.is_liouvillian:
+            cost = C.c_double()
+            L.check(L.lib.nq_force_liouvillian(ctx.h, self.loc.data_ptr(), self.gloc.data_ptr(), P, P, Ns, cc,
+                                               self._avg_complex(), self.gradC.data_ptr(), C.byref(cost)), ctx.h)
+            self.cost = cost.value
+        else:
+            L.check(L.lib.nq_force_ket(ctx.h, self.O.data_ptr(), P, P, Ns, oc, self.loc.data_ptr(),
+                                       self.gradC.data_ptr()), ctx.h)
+        if self.S is not None:
+            L.check(L.lib.nq_sr_setup(ctx.h, self.O.data_ptr(), P, P, Ns, self.Ns_total, oc, self.gradC.data_ptr(),
+                                      int(self.real_params), self.S.data_ptr(), self.F.data_ptr()), ctx.h)
+            if self.nranks > 1:      # C4 (global mean, quirk Q5)
+                ctx.allreduce_sum(self.S.data_ptr(), P * P, L.nq_dtype(self.sdtype))
+        else:
+            torch = _torch()
+            self.F.copy_(self.gradC.real if self.real_params else self.gradC)
+
+    def _avg_complex(self):
+        if self.avg.dtype == self.gradC.dtype:
+            return self.avg.data_ptr()
+        self._avgc = self.avg.to(self.gradC.dtype)
+        return self._avgc.data_ptr()
+
+    def statistics(self):
+        net, ctx = self.net, self.ctx
+        if self.is_liouvillian:
+            L.check(L.lib.nq_abs2(ctx.h, self.loc.data_ptr(), self.Ns, L.nq_dtype(net.cdtype), self.abs2.data_ptr()),
+                    ctx.h)
+            return stat_analysis(ctx, (self.abs2.data_ptr(), self.B, self.L, net.rdtype))
+        return stat_analysis(ctx, (self.loc.data_ptr(), self.B, self.L, net.cdtype))
+
+    def sample_(self, sample=True):
+        """sample!(is) -> (Measurement of the cost, self as the preconditioner cache)."""
+        if sample:
+            self.sample_states()
+        self.evaluate()
+        stat = self.statistics()
+        self.assemble()
+        return stat, self
+
+    def precondition_(self, iter_n=1):
+        """precondition!(cache, algo, iter) -> dw (device tensor; .cpu().numpy() for the host copy)."""
+        ctx, P, algo = self.ctx, self.net.P, self.algo
+        its = C.c_int64()
+        sd = L.nq_dtype(self.sdtype)
+        if self.S is not None:
+            solver = L.NQ_SOLVE_CHOLESKY if algo.algorithm == sr_cholesky else L.NQ_SOLVE_CG
+            st = L.lib.nq_sr_solve(ctx.h, self.S.data_ptr(), self.F.data_ptr(), P, sd, algo.sr_diag_shift, solver,
+                                   algo.sr_precision, 0, self.dw.data_ptr(), C.byref(its))
+        else:
+            st = L.lib.nq_sr_solve_matfree(ctx.h, self.O.data_ptr(), P, P, self.Ns, self.Ns_total,
+                                           L.nq_dtype(self.net.out_dtype), self.F.data_ptr(), int(self.real_params),
+                                           algo.sr_diag_shift, algo.sr_precision, 0, self.dw.data_ptr(), C.byref(its))
+        self.last_iters = its.value
+        if st == L.NQ_ERR_NOT_CONVERGED:       # reference: zero update after failed restarts
+            self.dw.zero_()
+        else:
+            L.check(st, ctx.h)
+        return self.dw
+
+    def update_(self, opt, dw=None):
+        dw = self.dw if dw is None else dw
+        net = self.net
+        if dw.dtype != _tdtype(net.dtype):
+            dw = dw.to(_tdtype(net.dtype))
+        L.check(L.lib.nq_update(net.h, dw.data_ptr(), float(opt.eta)), self.ctx.h)

@@ -19,3 +19,14 @@ def nq():
     """The product: ctypes bindings over libnqcuda (fails loudly if the library is missing)."""
     import nqcuda
     return nqcuda
+
+
+@pytest.fixture(scope="session")
+def ctx(nq):
+    """One libnqcuda context on cuda:0 sharing torch's current stream."""
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.cuda.init()
+    c = nq.Context(0, torch.cuda.current_stream().cuda_stream)
+    yield c
+    c.close()

@@ -1,0 +1,121 @@
+"""Shared helpers for the parity tests: matched (oracle, product) objects and error metrics."""
+import numpy as np
+
+from oracle import machines as OM
+from oracle import models as OMOD
+
+TOL = {np.dtype(np.float64): 1e-11, np.dtype(np.complex128): 1e-11,
+       np.dtype(np.float32): 1e-5, np.dtype(np.complex64): 1e-5}
+
+
+def assert_close(x, ref, tol, what=""):
+    """norm-wise relative error <= tol AND element-wise
+    |x - ref| <= tol * (|ref| + 1e-3 max|ref|)."""
+    x = np.asarray(x)
+    ref = np.asarray(ref)
+    assert x.shape == ref.shape, (what, x.shape, ref.shape)
+    assert np.all(np.isfinite(x)), what + ": non-finite values"
+    if ref.size == 0:
+        return
+    nrm = np.linalg.norm(ref.ravel())
+    err = np.linalg.norm((x - ref).ravel())
+    assert err <= tol * max(nrm, 1e-300), "%s: norm-wise rel err %.3e > %.1e" % (what, err / max(nrm, 1e-300), tol)
+    bound = tol * (np.abs(ref) + 1e-3 * np.abs(ref).max())
+    worst = np.max(np.abs(x - ref) - bound)
+    assert worst <= 0, "%s: element-wise excess %.3e" % (what, worst)
+
+
+def make_pair(nq, ctx, kind, hilb_kind, N, alpha, dtype, act=0, seed=1234, std=0.1, alpha_a=None):
+    """Oracle machine (float64/complex128 copy of the parameters as stored in `dtype`) + product machine."""
+    dtype = np.dtype(dtype)
+    cplx = dtype.kind == "c"
+    om = OM.random_machine(kind, N, alpha, act=act, complex_weights=cplx, seed=seed, std=std, alpha_a=alpha_a)
+    w = om.params().astype(dtype)
+    om.set_params(w.astype(np.complex128 if cplx else np.float64))     # oracle sees the rounded parameters
+    hilb = nq.HomogeneousSpin(N) if hilb_kind == "spin" else nq.HomogeneousFock(N)
+    if kind == "rbm":
+        pm = nq.RBM(ctx, hilb, dtype, alpha, act)
+    elif kind == "rbmsplit":
+        pm = nq.RBMSplit(ctx, hilb, dtype, alpha)
+    else:
+        pm = nq.NDM(ctx, hilb, dtype, alpha, alpha if alpha_a is None else alpha_a, act)
+    assert pm.P == om.P
+    pm.set_params(w)
+    return om, pm, hilb
+
+
+def ohilb(hilb_kind, N):
+    from oracle.hilbert import HomogeneousFock, HomogeneousSpin
+    return HomogeneousSpin(N) if hilb_kind == "spin" else HomogeneousFock(N)
+
+
+def rand_states(hilb_kind, N, B, seed):
+    return np.asfortranarray(OMOD.random_states(ohilb(hilb_kind, N), B, seed))
+
+
+# ---- the same physical models written with the PRODUCT's operator algebra --------------------
+def p_tfim_1d(nq, N, h=1.0, J=1.0):
+    hilb = nq.HomogeneousSpin(N)
+    H = nq.LocalOperator(hilb)
+    for i in range(1, N + 1):
+        H = H - h * nq.sigmax(hilb, i)
+        H = H + (J * nq.sigmaz(hilb, i)) * nq.sigmaz(hilb, i % N + 1)
+    return hilb, H
+
+
+def p_tfim_2d(nq, Lx, h=3.0, J=1.0):
+    N = Lx * Lx
+    hilb = nq.HomogeneousSpin(N)
+    H = nq.LocalOperator(hilb)
+    for i in range(1, N + 1):
+        H = H - h * nq.sigmax(hilb, i)
+    for y in range(Lx):
+        for x in range(Lx):
+            i = 1 + x + Lx * y
+            for j in (1 + (x + 1) % Lx + Lx * y, 1 + x + Lx * ((y + 1) % Lx)):
+                if i != j:
+                    H = H + (J * nq.sigmaz(hilb, i)) * nq.sigmaz(hilb, j)
+    return hilb, H
+
+
+def p_lindblad_ising_1d(nq, N, g=0.4, V=2.0, fock=True):
+    hilb = nq.HomogeneousFock(N, 2) if fock else nq.HomogeneousSpin(N)
+    H = nq.LocalOperator(hilb)
+    jumps = []
+    for i in range(1, N + 1):
+        H = H + (g / 2.0) * nq.sigmax(hilb, i)
+        H = H + ((V / 4.0) * nq.sigmaz(hilb, i)) * nq.sigmaz(hilb, i % N + 1)
+        jumps.append(nq.sigmam(hilb, i))
+    return hilb, H, jumps, nq.liouvillian(H, jumps)
+
+
+def enumerate_tables(tb, bits_row, bits_col=None):
+    """Host enumeration of the flattened tables for ONE configuration given as digit arrays
+    (what the device kernel does; used by CPU tests of the table builder)."""
+    out = []
+    site_ptr = np.concatenate([[0], np.cumsum(tb["part_nsites"])])
+    row0 = np.concatenate([[0], np.cumsum(2 ** tb["part_nsites"].astype(np.int64))])
+
+    def rows(p, bits):
+        s = tb["part_sites"][site_ptr[p]:site_ptr[p + 1]]
+        r = sum(int(bits[j]) << i for i, j in enumerate(s))
+        e0, e1 = tb["row_ptr"][row0[p] + r], tb["row_ptr"][row0[p] + r + 1]
+        res = []
+        for e in range(e0, e1):
+            m = 0
+            for i, j in enumerate(s):
+                if (int(tb["entry_flip"][e]) >> i) & 1:
+                    m |= 1 << int(j)
+            res.append((complex(tb["entry_mel"][e]), m))
+        return res
+    for t in range(tb["n_terms"]):
+        Lp, Rp = int(tb["term_left"][t]), int(tb["term_right"][t])
+        if Lp >= 0 and Rp < 0:
+            out += [(m, f, 0) for m, f in rows(Lp, bits_row)]
+        elif Lp < 0 and Rp >= 0:
+            out += [(m, 0, f) for m, f in rows(Rp, bits_col)]
+        else:
+            for ml, fl in rows(Lp, bits_row):
+                for mr, fr in rows(Rp, bits_col):
+                    out.append((ml * mr, fl, fr))
+    return out

@@ -1,0 +1,169 @@
+"""GPU parity: centring, force vectors, S assembly (DMMA SYRK/HERK), Cholesky / CG solves, chain
+statistics (K6-K9) vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import sr as OSR
+from oracle import stats as OST
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    """numpy [P, Ns] (Fortran) -> torch device tensor [Ns, P] sharing the column-major layout."""
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a).T)).cuda()
+
+
+def _rand(rng, shape, dtype):
+    dtype = np.dtype(dtype)
+    if dtype.kind == "c":
+        return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(dtype)
+    return rng.standard_normal(shape).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype,P,Ns,real_params", [
+    (np.complex128, 230, 1000, False), (np.complex128, 576, 2000, True), (np.float64, 130, 515, True),
+    (np.complex64, 200, 777, False), (np.float32, 129, 600, True), (np.complex128, 300, 70, False),
+    (np.complex128, 1, 9, False)])
+def test_center_force_setup(nq, ctx, dtype, P, Ns, real_params):
+    L = nq._lib
+    rng = np.random.default_rng(5)
+    dtype = np.dtype(dtype)
+    cdt = np.dtype(np.complex64 if dtype in (np.dtype(np.float32), np.dtype(np.complex64)) else np.complex128)
+    tol = H.TOL[dtype]
+    O = _rand(rng, (P, Ns), dtype) + dtype.type(0.5)
+    O64 = O.astype(np.complex128 if dtype.kind == "c" else np.float64)
+    E = _rand(rng, Ns, cdt)
+    dO = _dev(O)
+    avg = np.zeros(P, dtype)
+    L.check(L.lib.nq_center(ctx.h, dO.data_ptr(), P, P, Ns, L.nq_dtype(dtype), L.ptr(avg)), ctx.h)
+    ravg, rOc = OSR.center(O64)
+    H.assert_close(avg, ravg, tol, "<O>")
+    # centred values are differences of O(1) numbers: tolerance relative to |O|
+    Oc = dO.cpu().numpy().T
+    assert np.max(np.abs(Oc - rOc)) <= 4 * tol * np.abs(O64).max()
+    Oc64 = Oc.astype(O64.dtype)
+    # ket force
+    g = np.zeros(P, cdt)
+    L.check(L.lib.nq_force_ket(ctx.h, dO.data_ptr(), P, P, Ns, L.nq_dtype(dtype), L.ptr(E), L.ptr(g)), ctx.h)
+    rg = OSR.force_ket(E.astype(np.complex128), Oc64)
+    H.assert_close(g, rg, 20 * tol, "grad C (ket)")
+    # S, F
+    sdt = np.dtype(dtype if (dtype.kind == "c" and not real_params) else (np.float32 if cdt == np.complex64 else np.float64))
+    S = np.zeros((P, P), sdt, order="F")
+    F = np.zeros(P, sdt)
+    L.check(L.lib.nq_sr_setup(ctx.h, dO.data_ptr(), P, P, Ns, Ns, L.nq_dtype(dtype), L.ptr(g), int(real_params),
+                              L.ptr(S), L.ptr(F)), ctx.h)
+    rS, rF = OSR.sr_setup(Oc64, g.astype(np.complex128), real_params)
+    H.assert_close(S, rS, tol, "S")
+    H.assert_close(F, rF, tol, "F")
+    if sdt.kind == "c":
+        assert np.allclose(S, S.conj().T, atol=0)          # Hermitian by construction (mirrored tiles)
+
+
+def test_force_liouvillian(nq, ctx):
+    L = nq._lib
+    rng = np.random.default_rng(6)
+    P, Ns = 200, 640
+    Lloc = _rand(rng, Ns, np.complex128)
+    gL = _rand(rng, (P, Ns), np.complex128)
+    avg = _rand(rng, P, np.complex128)
+    g = np.zeros(P, np.complex128)
+    import ctypes as C
+    cost = C.c_double()
+    dg = _dev(gL)
+    L.check(L.lib.nq_force_liouvillian(ctx.h, L.ptr(Lloc), dg.data_ptr(), P, P, Ns, L.NQ_C128, L.ptr(avg), L.ptr(g),
+                                       C.byref(cost)), ctx.h)
+    H.assert_close(g, OSR.force_liouvillian(Lloc, gL, avg), 1e-11, "grad C (Liouvillian)")
+    assert abs(cost.value - np.mean(np.abs(Lloc) ** 2)) < 1e-12 * cost.value
+
+
+def _spd(rng, P, cplx):
+    Ns = 3 * P
+    O = rng.standard_normal((P, Ns)) + (1j * rng.standard_normal((P, Ns)) if cplx else 0)
+    S = (O.conj() @ O.T) / Ns
+    return np.asfortranarray(S)
+
+
+@pytest.mark.parametrize("P,cplx", [(230, True), (576, False), (33, False), (1, True), (100, True)])
+def test_cholesky_and_cg_solve(nq, ctx, P, cplx):
+    import ctypes as C
+    L = nq._lib
+    rng = np.random.default_rng(7)
+    S = _spd(rng, P, cplx)
+    F = rng.standard_normal(P) + (1j * rng.standard_normal(P) if cplx else 0)
+    eps = OSR.eps_f32(0.001)
+    ref = OSR.solve_cholesky(S, F, eps)
+    sd = L.NQ_C128 if cplx else L.NQ_F64
+    for algo, tol in ((L.NQ_SOLVE_CHOLESKY, 1e-10), (L.NQ_SOLVE_CG, 1e-8)):
+        Sw = S.copy(order="F")
+        dw = np.zeros_like(F)
+        its = C.c_int64()
+        L.check(L.lib.nq_sr_solve(ctx.h, L.ptr(Sw), L.ptr(F), P, sd, eps, algo, 1e-12, 0, L.ptr(dw), C.byref(its)), ctx.h)
+        cond = np.linalg.cond(S + eps * np.eye(P))
+        assert np.linalg.norm(dw - ref) <= max(tol, 1e-15 * cond) * np.linalg.norm(ref), (algo, its.value)
+        if algo == L.NQ_SOLVE_CG:
+            assert 0 < its.value <= 10 * P
+            x, it_ref, ok = OSR.solve_cg_explicit(S, F, eps, 1e-12)
+            assert abs(its.value - it_ref) <= 2          # same stopping rule as the oracle (unpinned in the reference)
+
+
+def test_cholesky_not_posdef_and_cg_not_converged(nq, ctx):
+    import ctypes as C
+    L = nq._lib
+    S = -np.eye(40, order="F")
+    S[0, 0] = 1.0
+    F = np.ones(40)
+    dw = np.zeros(40)
+    its = C.c_int64()
+    st = L.lib.nq_sr_solve(ctx.h, L.ptr(S.copy(order="F")), L.ptr(F), 40, L.NQ_F64, 0.0, L.NQ_SOLVE_CHOLESKY, 0.0, 0,
+                           L.ptr(dw), C.byref(its))
+    assert st == L.NQ_ERR_NOT_POSDEF
+    with pytest.raises(nq.PosDefException):
+        L.check(st, ctx.h)
+    info = C.c_int64()
+    L.lib.nq_ctx_last_info(ctx.h, C.byref(info))
+    assert info.value == 1
+    rng = np.random.default_rng(1)
+    S = _spd(rng, 50, False)
+    st = L.lib.nq_sr_solve(ctx.h, L.ptr(S), L.ptr(np.ones(50)), 50, L.NQ_F64, 0.0, L.NQ_SOLVE_CG, 1e-30, 3,
+                           L.ptr(np.zeros(50)), C.byref(its))
+    assert st == L.NQ_ERR_NOT_CONVERGED and its.value == 3
+
+
+@pytest.mark.parametrize("dtype,real_params", [(np.complex128, False), (np.complex128, True), (np.float64, True)])
+def test_matrix_free_cg(nq, ctx, dtype, real_params):
+    import ctypes as C
+    L = nq._lib
+    rng = np.random.default_rng(8)
+    P, Ns = 150, 900
+    O = _rand(rng, (P, Ns), dtype)
+    O64 = O.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64)
+    _, Oc = OSR.center(O64)
+    cplx_out = np.dtype(dtype).kind == "c" and not real_params
+    F = rng.standard_normal(P) + (1j * rng.standard_normal(P) if cplx_out else 0)
+    eps = 0.01
+    ref, it_ref, ok = OSR.solve_cg(Oc, F, eps, 1e-10, real_params)
+    assert ok
+    dOc = _dev(Oc.astype(dtype))
+    dw = np.zeros_like(F)
+    its = C.c_int64()
+    L.check(L.lib.nq_sr_solve_matfree(ctx.h, dOc.data_ptr(), P, P, Ns, Ns, L.nq_dtype(dtype), L.ptr(F), int(real_params),
+                                      eps, 1e-10, 0, L.ptr(dw), C.byref(its)), ctx.h)
+    assert np.linalg.norm(dw - ref) <= 1e-8 * np.linalg.norm(ref)
+    assert abs(its.value - it_ref) <= 2
+    S, _ = OSR.sr_setup(Oc, F, real_params)
+    assert np.linalg.norm(dw - np.linalg.solve(S + eps * np.eye(P), F)) <= 1e-7 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.float64, np.complex64])
+def test_stat_analysis(nq, ctx, dtype):
+    rng = np.random.default_rng(9)
+    v = _rand(rng, (16, 125), dtype)
+    m = nq.stat_analysis(ctx, v)
+    r = OST.stat_analysis(v.astype(np.complex128))
+    tol = 1e-5 if np.dtype(dtype) == np.complex64 else 1e-12
+    for a, b in ((m.mean, r["mean"]), (m.error, r["error"]), (m.variance, r["variance"]), (m.tau, r["tau"]), (m.R, r["R"])):
+        assert abs(a - b) <= tol * max(1.0, abs(b))
