@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for libnqcuda.
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on):
+    dissipative Ising 1D, N=16, g=0.4, V=2, gamma=1 (L_i = sigma^-_i), NDM alpha_h=alpha_a=2 (softplus),
+    Float64, 65 536 samples per iteration = 4096 chains x 16 stored samples, sharded over the GPUs
+    (strong scaling: the global sample count is fixed), SR eps=0.001 Cholesky, Descent(0.01).
+
+Metric: MC samples/s of {log rho + gradient rows O, local Liouvillian estimator L_loc + grad L_loc}
+("eval+grad+local estimator"), inputs resident in HBM; `sr_iteration` reports seconds per full SR
+iteration (sampling + eval/grad + estimator + centring/force + S assembly + all-reduce + solve + update).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+For N>1 the driver launches it under torchrun; one rank per GPU, NCCL.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "neuralquantum.jl_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOAD = dict(N=16, alpha=2, g=0.4, V=2.0, chains=4096, L=16, passes=17, burn=100, eps=0.001, eta=0.01)
+WORKLOAD_NAME = ("cfg4: dissipative Ising 1D N=16 steady state, NDM alpha=2 (softplus, Float64), "
+                 "65536 samples/iter = 4096 chains x 16, SR eps=1e-3 Cholesky")
+METRIC = "MC samples/s (eval+grad+local estimator)"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (the one place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    n, seed = args
+    from oracle import estimators as OE, machines as OM
+    from oracle.models import lindblad_ising_1d, random_states
+    w = WORKLOAD
+    hilb, _, _, liouv = lindblad_ising_1d(w["N"], w["g"], w["V"])
+    net = OM.random_machine("ndm", w["N"], w["alpha"], seed=1234, std=0.1)
+    sr_, sc_ = random_states(hilb, n, seed), random_states(hilb, n, seed + 1)
+    t0 = time.perf_counter()
+    out, O = net.logpsi_grad(sr_, sc_)
+    OE.local_grad_super(net, liouv, sr_, sc_, out)
+    return time.perf_counter() - t0
+
+
+def cpu_samples_per_s(n_samples, procs):
+    """eval+grad+local estimator of the oracle port over n_samples configurations, sharded over
+    `procs` worker processes (the reference's threads+MPI = chain-sharded workers)."""
+    import multiprocessing as mp
+    per = max(1, n_samples // procs)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_worker, [(2, 1)] * procs)                 # import + warm-up
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(per, 100 + i) for i in range(procs)])
+        dt = time.perf_counter() - t0
+    return per * procs / dt, per * procs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    n = 16 * procs
+    for _ in range(args.warmup):
+        cpu_samples_per_s(procs * 2, procs)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, used = cpu_samples_per_s(n, procs)
+        vals.append(v)
+    dt = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    sample = "%d configurations per step over %d worker processes (NumPy oracle port; Julia unavailable)" % (used, procs)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
+        out["sm_mhz"] = float(np.median(sm)) if sm else None
+        out["sm_max_mhz"] = float(rows[0][2]) if rows[0][2].strip().replace(".", "").isdigit() else None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in rows:
+            for nm, v in zip(names, r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(nm)
+        out["reasons"] = sorted(reasons)
+        out["power_w_max"] = max(float(r[3]) for r in rows if r[3].strip().replace(".", "").isdigit())
+        return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import nqcuda as nq
+    import helpers as H
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched under torchrun with %d ranks" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = nq.Context(local, torch.cuda.current_stream().cuda_stream)
+    if world > 1:
+        box = [nq.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(world, rank, box[0])
+
+    w = WORKLOAD
+    N, Lc = w["N"], w["L"]
+    B = w["chains"] // world                       # chains of this rank (strong scaling)
+    Ns = B * Lc
+    Ns_global = Ns * world
+    hilb, _, _, liouv = H.p_lindblad_ising_1d(nq, N, w["g"], w["V"])
+    net = nq.NDM(ctx, hilb, np.float64, w["alpha"], w["alpha"], nq.af_softplus, seed=1234)
+    nq.init_random_pars_(net, sigma=0.01, seed=1234)
+    smp = nq.MetropolisSampler(nq.LocalRule(), Lc * world, w["passes"] - 1, burn=w["burn"], seed=99)
+    bs = nq.BatchedSampler(net, smp, liouv, nq.SR(np.float32, eps=w["eps"], algorithm="sr_cholesky"), batch_sz=B,
+                           chain_length=Lc)
+    P = net.P
+
+    # synthetic configurations (uniform, seed 4321 + rank), resident on the device before timing
+    rng = np.random.Generator(np.random.Philox(4321 + rank))
+    host_r = torch.empty((Ns, N), dtype=torch.float64).pin_memory()
+    host_c = torch.empty((Ns, N), dtype=torch.float64).pin_memory()
+    host_r.numpy()[:] = rng.integers(0, 2, size=(Ns, N))
+    host_c.numpy()[:] = rng.integers(0, 2, size=(Ns, N))
+    host_loc = torch.empty(Ns, dtype=torch.complex128).pin_memory()
+    sig = (host_r.numpy().T.reshape(N, B, Lc, order="F"), host_c.numpy().T.reshape(N, B, Lc, order="F"))
+    bs.set_samples(sig)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; device time (CUDA events), max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- headline: eval + grad + local estimator on resident configurations ----
+    for _ in range(max(3, args.warmup)):
+        bs.evaluate()
+    clocks = ClockSampler(local)
+    l0 = ctx.launches
+    ms = timed(bs.evaluate, args.steps)
+    launches = ctx.launches - l0
+    value = Ns_global * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel durations inside the same loop (events around each launch) ----
+    pc = bs.pcol.data_ptr()
+    L_ = nq._lib
+
+    def k_evalgrad():
+        L_.check(L_.lib.nq_logpsi_grad_packed(net.h, bs.prow.data_ptr(), pc, Ns, bs.logpsi.data_ptr(), bs.O.data_ptr(), P), ctx.h)
+
+    def k_local():
+        L_.check(L_.lib.nq_local_grad_packed(net.h, bs.op.h, bs.prow.data_ptr(), pc, Ns, bs.loc.data_ptr(), bs.gloc.data_ptr(), P), ctx.h)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    for s in range(args.steps):
+        ev[s][0].record(); k_evalgrad(); ev[s][1].record(); k_local(); ev[s][2].record()
+    barrier()
+    t_eval = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    t_loc = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    clk = clocks.stop()
+
+    # ---- full SR iteration ----
+    opt = nq.Descent(w["eta"])
+
+    def sr_iter():
+        bs.sample_()
+        bs.precondition_()
+        bs.update_(opt)
+    phases = {}
+
+    def phase(name, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        phases[name] = phases.get(name, 0.0) + a.elapsed_time(b)
+    sr_iter()
+    n_it = max(2, min(args.steps, 5))
+    ms_sr = timed(sr_iter, n_it)
+    for _ in range(2):
+        phase("sampler", bs.sample_states)
+        phase("evalgrad+estimator", bs.evaluate)
+        phase("statistics", bs.statistics)
+        phase("centre+force+S", bs.assemble)
+        phase("solve", bs.precondition_)
+        phase("update", lambda: bs.update_(opt))
+    phases = {k: v / 2 for k, v in phases.items()}
+    # restore the synthetic configurations (the SR iterations above sampled new ones)
+    bs.set_samples(sig)
+
+    # ---- e2e: public API with HOST buffers (pinned), H2D of the configurations and D2H of L_loc inside ----
+    def e2e_step():
+        bs.set_samples(sig)
+        bs.evaluate()
+        host_loc.copy_(bs.loc, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = Ns_global * args.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk, pk_kind = peaks()
+    es = 16
+    bytes_eval = Ns * (P * es + es + 2 * 8)               # O row + log rho + two packed words per configuration
+    bytes_loc = Ns * (P * es + es + 2 * 8)                # grad L_loc row + L_loc + packed words
+    dom = ("local_ndm_kernel<double,softplus,grad>", t_loc, bytes_loc) if t_loc >= t_eval else \
+          ("ndm_evalgrad_kernel<double,softplus,grad>", t_eval, bytes_eval)
+    ach = dom[2] / (dom[1] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
+            "ms_per_launch": dom[1], "algorithmic_bytes_per_launch": dom[2],
+            "all": {"ndm_evalgrad_kernel": {"ms": t_eval, "GB/s": bytes_eval / (t_eval * 1e-3) / 1e9,
+                                            "frac": bytes_eval / (t_eval * 1e-3) / 1e9 / pk["hbm_gbs"]},
+                    "local_ndm_kernel": {"ms": t_loc, "GB/s": bytes_loc / (t_loc * 1e-3) / 1e9,
+                                         "frac": bytes_loc / (t_loc * 1e-3) / 1e9 / pk["hbm_gbs"]}}}
+    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "chains_per_gpu": B, "stored_per_chain": Lc, "P": P,
+                       "parallelism": "dp%d (chains sharded, NCCL all-reduce of <O>, F, S)" % world,
+                       "l2": "every step writes O and grad L_loc (%.2f GB per GPU) >> 126 MB L2" % (2 * Ns * P * es / 1e9)},
+            "sr_iteration": {"value": ms_sr * 1e-3 / n_it, "unit": "s", "iterations": n_it, "phases_ms": phases,
+                             "includes": "sampler(burn=100,passes=17)+eval/grad+estimator+centre+force+S(+allreduce)+Cholesky+update"},
+            "roofline": roof, "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(2 * Ns * N * 8),
+                    "d2h_bytes_per_step": int(Ns * 16), "ms_per_step": ms_e2e / args.steps}}
+    if world == 1 and not args.no_cpu:
+        procs = os.cpu_count() or 1
+        v, used = cpu_samples_per_s(8 * procs, procs)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": procs, "kind": "port",
+                                "sample": "%d configurations of the same workload over %d worker processes "
+                                          "(NumPy oracle port of the reference algorithm; Julia unavailable)" % (used, procs)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="nqcuda", choices=["nqcuda", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

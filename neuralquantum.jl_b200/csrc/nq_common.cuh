@@ -64,7 +64,7 @@ bool nq_is_device_ptr(const void* p);
 // Staging of caller buffers that may live on the host.
 struct NqStage {
     nq_ctx_t ctx;
-    struct Out { void* user; void* dev; size_t bytes; };
+    struct Out { void* user; void* dev; size_t bytes; size_t width, pitch, rows; };
     std::vector<Out> outs;
     int status = NQ_OK;
     explicit NqStage(nq_ctx_t c) : ctx(c) {}
@@ -84,7 +84,17 @@ struct NqStage {
         if (nq_is_device_ptr(p)) return p;
         void* d = nq_scratch(ctx, slot, bytes);
         if (!d) { status = NQ_ERR_ALLOC; return nullptr; }
-        outs.push_back({p, d, bytes});
+        outs.push_back({p, d, bytes, 0, 0, 0});
+        return d;
+    }
+    // pitched output (leading dimension > row width): only the [width x rows] payload is written back
+    void* out2d(int slot, void* p, size_t width, size_t pitch, size_t rows) {
+        if (!p || rows == 0) return p;
+        if (nq_is_device_ptr(p)) return p;
+        if (width == pitch) return out(slot, p, pitch * rows);
+        void* d = nq_scratch(ctx, slot, pitch * rows);
+        if (!d) { status = NQ_ERR_ALLOC; return nullptr; }
+        outs.push_back({p, d, pitch * rows, width, pitch, rows});
         return d;
     }
     // copy staged outputs back; synchronises only when something went to the host
@@ -92,7 +102,8 @@ struct NqStage {
         if (status != NQ_OK) return status;
         if (outs.empty()) return NQ_OK;
         for (auto& o : outs) {
-            cudaError_t e = cudaMemcpyAsync(o.user, o.dev, o.bytes, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaError_t e = o.rows ? cudaMemcpy2DAsync(o.user, o.pitch, o.dev, o.pitch, o.width, o.rows, cudaMemcpyDeviceToHost, ctx->stream)
+                                   : cudaMemcpyAsync(o.user, o.dev, o.bytes, cudaMemcpyDeviceToHost, ctx->stream);
             if (e != cudaSuccess) return nq_fail(ctx, NQ_ERR_CUDA, "D2H copy: %s", cudaGetErrorString(e));
         }
         cudaError_t e = cudaStreamSynchronize(ctx->stream);

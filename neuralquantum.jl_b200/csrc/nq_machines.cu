@@ -493,7 +493,7 @@ extern "C" int nq_logpsi_grad(nq_machine_t m, const void* srow, const void* scol
     NQ_CHECK(nq_stage_pack(m, st, srow, scol, sdtype, B, &pr, &pc));
     size_t es = nq_dtype_size(m->out_dtype);
     void* dout = st.out(SL_OUT0, out, (size_t)B * es);
-    void* dO = O ? st.out(SL_OUT1, O, (size_t)B * ldO * es) : nullptr;
+    void* dO = O ? st.out2d(SL_OUT1, O, (size_t)m->P * es, (size_t)ldO * es, (size_t)B) : nullptr;
     if (st.status != NQ_OK) return st.status;
     NQ_CHECK(nq_machine_eval_device(m, pr, pc, B, dout, dO, ldO));
     return st.finish();
@@ -540,7 +540,7 @@ extern "C" int nq_logpsi_grad_packed(nq_machine_t m, const uint64_t* prow, const
     const uint64_t* pr = (const uint64_t*)st.in(SL_PROW, prow, pbytes);
     const uint64_t* pc = pcol ? (const uint64_t*)st.in(SL_PCOL, pcol, pbytes) : nullptr;
     void* dout = st.out(SL_OUT0, out, (size_t)B * es);
-    void* dO = O ? st.out(SL_OUT1, O, (size_t)B * ldO * es) : nullptr;
+    void* dO = O ? st.out2d(SL_OUT1, O, (size_t)m->P * es, (size_t)ldO * es, (size_t)B) : nullptr;
     if (st.status != NQ_OK) return st.status;
     NQ_CHECK(nq_machine_eval_device(m, pr, pc, B, dout, dO, ldO));
     return st.finish();

@@ -885,7 +885,7 @@ static int local_common(nq_machine_t m, nq_operator_t op, const void* srow, cons
     }
     size_t cs = nq_dtype_size(nq_complex_of(m->dtype));
     void* dl = st.out(SL_OUT0, out_loc, (size_t)B * cs);
-    void* dg = out_g ? st.out(SL_OUT1, out_g, (size_t)B * ld * cs) : nullptr;
+    void* dg = out_g ? st.out2d(SL_OUT1, out_g, (size_t)m->P * cs, (size_t)ld * cs, (size_t)B) : nullptr;
     if (st.status != NQ_OK) return st.status;
     NQ_CHECK(nq_local_device(m, op, pr, pc, B, dl, dg, ld));
     return st.finish();

@@ -14,6 +14,7 @@
 #include "nq_internal.cuh"
 
 struct nq_sampler_s {
+    nq_ctx_t ctx;
     nq_machine_t m;
     int64_t B;
     int passes;
@@ -365,7 +366,7 @@ extern "C" int nq_sampler_create(nq_machine_t m, int64_t B, int passes, uint64_t
     if (B <= 0 || passes <= 0) return nq_fail(ctx, NQ_ERR_ARG, "B and passes must be positive");
     NQ_CUDA(ctx, cudaSetDevice(ctx->device));
     nq_sampler_t s = new nq_sampler_s();
-    s->m = m; s->B = B;
+    s->ctx = ctx; s->m = m; s->B = B;
     s->passes = (passes % 2 == 0) ? passes + 1 : passes;   // Metropolis.jl:30-38
     s->seed = seed; s->chain_offset = chain_offset; s->pass_base = 0; s->passes_done = 0;
     s->prow = s->pcol = nullptr; s->accepted = nullptr;
@@ -388,8 +389,8 @@ extern "C" int nq_sampler_create(nq_machine_t m, int64_t B, int passes, uint64_t
 
 extern "C" int nq_sampler_destroy(nq_sampler_t s) {
     if (!s) return NQ_ERR_ARG;
-    cudaSetDevice(s->m->ctx->device);
-    cudaStreamSynchronize(s->m->ctx->stream);
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
     cudaFree(s->prow); cudaFree(s->pcol); cudaFree(s->accepted);
     delete s;
     return NQ_OK;

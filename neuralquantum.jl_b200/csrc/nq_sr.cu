@@ -418,7 +418,7 @@ template <typename E> __device__ __forceinline__ E bcast(E v, int src) {
 // forward L y = b (right-looking, coalesced row updates) then backward L^H x = y (left-looking,
 // coalesced column dot products); a single CTA walks the block columns.
 template <typename E>
-__global__ void chol_solve_kernel(const E* __restrict__ L, int64_t P, E* __restrict__ x) {
+__global__ void __launch_bounds__(512) chol_solve_kernel(const E* __restrict__ L, int64_t P, E* __restrict__ x) {
     __shared__ E blk[NB];
     __shared__ E Lb[NB][NB + 1];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
@@ -493,7 +493,7 @@ int cholesky_solve(nq_ctx_t ctx, E* A, int64_t P, E* x, int* dinfo) {
             NQ_LAUNCH(ctx, chol_update_kernel<E>, (unsigned)(nt * (nt + 1) / 2), 256, 0, A, P, j0, nb);
         }
     }
-    NQ_LAUNCH(ctx, chol_solve_kernel<E>, 1, 1024, 0, (const E*)A, P, x);
+    NQ_LAUNCH(ctx, chol_solve_kernel<E>, 1, 512, 0, (const E*)A, P, x);
     return NQ_OK;
 }
 

@@ -53,6 +53,7 @@ class Machine:
         try:
             if self.h and self.ctx.h:
                 L.lib.nq_machine_destroy(self.h)
+            self.h = None
         except Exception:
             pass
 

@@ -272,6 +272,7 @@ class DeviceOperator:
         try:
             if self.h and self.ctx.h:
                 L.lib.nq_operator_destroy(self.h)
+            self.h = None
         except Exception:
             pass
 

@@ -42,6 +42,7 @@ class MetropolisSamplerCache:
         try:
             if self.h and self.net.ctx.h:
                 L.lib.nq_sampler_destroy(self.h)
+            self.h = None
         except Exception:
             pass
 

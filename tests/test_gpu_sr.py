@@ -118,7 +118,8 @@ def test_cholesky_not_posdef_and_cg_not_converged(nq, ctx):
     F = np.ones(40)
     dw = np.zeros(40)
     its = C.c_int64()
-    st = L.lib.nq_sr_solve(ctx.h, L.ptr(S.copy(order="F")), L.ptr(F), 40, L.NQ_F64, 0.0, L.NQ_SOLVE_CHOLESKY, 0.0, 0,
+    Sw = S.copy(order="F")
+    st = L.lib.nq_sr_solve(ctx.h, L.ptr(Sw), L.ptr(F), 40, L.NQ_F64, 0.0, L.NQ_SOLVE_CHOLESKY, 0.0, 0,
                            L.ptr(dw), C.byref(its))
     assert st == L.NQ_ERR_NOT_POSDEF
     with pytest.raises(nq.PosDefException):
@@ -128,8 +129,9 @@ def test_cholesky_not_posdef_and_cg_not_converged(nq, ctx):
     assert info.value == 1
     rng = np.random.default_rng(1)
     S = _spd(rng, 50, False)
-    st = L.lib.nq_sr_solve(ctx.h, L.ptr(S), L.ptr(np.ones(50)), 50, L.NQ_F64, 0.0, L.NQ_SOLVE_CG, 1e-30, 3,
-                           L.ptr(np.zeros(50)), C.byref(its))
+    F50, dw50 = np.ones(50), np.zeros(50)
+    st = L.lib.nq_sr_solve(ctx.h, L.ptr(S), L.ptr(F50), 50, L.NQ_F64, 0.0, L.NQ_SOLVE_CG, 1e-30, 3,
+                           L.ptr(dw50), C.byref(its))
     assert st == L.NQ_ERR_NOT_CONVERGED and its.value == 3
 
 
