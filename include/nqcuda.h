@@ -66,7 +66,7 @@ typedef struct nq_sampler_s* nq_sampler_t;
 /* ======================================================================================
  * Context.  One context = one device + one stream.  ref: one sampler object per task/rank
  * (Parallel/Threads/threads_wrappers.jl:14-31, Parallel/MPI/mpi.jl).
- * `stream` is a cudaStream_t (NULL: the library creates its own non-blocking stream).
+ * `stream` is a cudaStream_t used as given for every launch and copy (NULL = the CUDA default stream).
  * ==================================================================================== */
 int nq_version(void);
 const char* nq_status_string(int status);

@@ -64,11 +64,9 @@ extern "C" int nq_ctx_create(int device, void* stream, nq_ctx_t* out) {
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return NQ_ERR_CUDA; }
     nq_ctx_t c = new nq_ctx_s();
     c->device = device;
-    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
-    else {
-        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NQ_ERR_CUDA; }
-        c->own_stream = true;
-    }
+    // the handle is used as given; NULL is CUDA's default stream (which is also torch's default current stream)
+    c->stream = (cudaStream_t)stream;
+    c->own_stream = false;
     cudaDeviceProp p;
     if (cudaGetDeviceProperties(&p, device) == cudaSuccess) {
         c->num_sms = p.multiProcessorCount;

@@ -12,7 +12,7 @@ from . import _lib as L
 
 class Context:
     """One device + one stream (nq_ctx_t).  `stream` is a raw cudaStream_t address (e.g.
-    torch.cuda.current_stream().cuda_stream) or None for a library-owned stream."""
+    torch.cuda.current_stream().cuda_stream); None = the CUDA default stream."""
 
     def __init__(self, device=0, stream=None):
         h = C.c_void_p()
