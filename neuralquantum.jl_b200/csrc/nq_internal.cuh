@@ -30,6 +30,7 @@ struct nq_operator_s {
     int64_t n_rows, n_entries;
     int64_t max_conn;
     int max_part_sites;
+    int site_local;         // every connection flips at most one site index
     // device tables
     int32_t* part_nsites;   // [n_parts]
     int32_t* part_site_ptr; // [n_parts+1] offsets into part_sites

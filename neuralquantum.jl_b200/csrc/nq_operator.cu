@@ -201,526 +201,7 @@ __device__ inline unsigned char* conn_list_carve(unsigned char* p, int cap, int 
     return p;
 }
 
-constexpr int CB = 4;   // connections processed per batch (ILP + one block reduction per batch)
-
-// block-wide sum of CB complex numbers; result broadcast to every thread (2 barriers)
-template <typename T>
-__device__ __forceinline__ void block_sum_cb(cx<T> (&acc)[CB], cx<T>* red /* [32][CB] */) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-    for (int i = 0; i < CB; i++) {
-        cx<T> v = warp_sum(acc[i]);
-        if (lane == 0) red[warp * CB + i] = v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < CB; i++) {
-        cx<T> v = red[i];
-        for (int w = 1; w < nw; w++) v += red[w * CB + i];
-        acc[i] = v;
-    }
-    __syncthreads();
-}
-
-// ---------------------------------------------------------------------------------------
-// RBM (ket, scalar only) and RBMSplit (super; scalar and gradient)
-// ---------------------------------------------------------------------------------------
-template <typename E, int ACT, bool DOUBLED, bool GRAD>
-__global__ void local_rbm_kernel(OpDev op, const E* __restrict__ par, const uint64_t* __restrict__ prow,
-                                 const uint64_t* __restrict__ pcol, int64_t B, int N, int M, int hilb,
-                                 int cap, cx<typename elem_traits<E>::real>* __restrict__ out_loc,
-                                 cx<typename elem_traits<E>::real>* __restrict__ out_g, int64_t ld) {
-    typedef typename elem_traits<E>::real T;
-    typedef cx<T> C;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, NT = blockDim.x;
-    const int W64 = (N + 63) >> 6;
-    const int64_t b = blockIdx.x;
-    const uint64_t* rb = prow + b * W64;
-    const uint64_t* cb = DOUBLED ? pcol + b * W64 : nullptr;
-
-    ConnList<T> cl;
-    unsigned char* p = conn_list_carve<T>(smem_raw, cap, op.n_terms, cl);
-    C* red = (C*)p; p += 32 * CB * sizeof(C);
-    E* th = (E*)p; p += align16<T>((size_t)M * sizeof(E));       // theta_k
-    E* fk = (E*)p; p += align16<T>((size_t)M * sizeof(E));       // f(theta_k)
-    E* dc = (E*)p; p += align16<T>((size_t)CB * M * sizeof(E));  // d^c_k of the current batch
-    C* Ak = (C*)p; p += align16<T>((size_t)(GRAD ? M : 0) * sizeof(C));  // sum_c w_c d^c_k
-    C* vis = (C*)p; p += align16<T>((size_t)(GRAD ? 2 * N : 0) * sizeof(C)); // sum_{c flips j} w_c dv_j
-    C* g = (C*)p;                                                // staged output row [P]
-
-    const int64_t off_b = DOUBLED ? 2 * N : N;
-    const int64_t off_Wr = off_b + M, off_Wc = off_Wr + (int64_t)M * N;
-    const int64_t P = DOUBLED ? off_Wc + (int64_t)M * N : off_Wc;
-    const E* __restrict__ Wr = par + off_Wr;
-    const E* __restrict__ Wc = par + off_Wc;
-
-    C wdiag;
-    const int nconn = build_conn_list<T>(op, rb, cb, cl, &wdiag);
-
-    // base pre-activations
-    for (int k = tid; k < M; k += NT) {
-        E t = par[off_b + k];
-        for (int j = 0; j < N; j++) {
-            t += rscale(digit_value<T>(hilb, get_bit(rb, j)), Wr[k + (int64_t)M * j]);
-            if (DOUBLED) t += rscale(digit_value<T>(hilb, get_bit(cb, j)), Wc[k + (int64_t)M * j]);
-        }
-        E f, d;
-        act_eval<ACT>(t, f, d);
-        th[k] = t; fk[k] = f;
-        if (GRAD) Ak[k] = wdiag * to_cx(d);
-    }
-    if (GRAD) {
-        for (int64_t i = tid; i < P; i += NT) g[i] = C(T(0), T(0));
-        for (int i = tid; i < 2 * N; i += NT) vis[i] = C(T(0), T(0));
-    }
-    __syncthreads();
-
-    C wtot = wdiag;
-    for (int c0 = 0; c0 < nconn; c0 += CB) {
-        C acc[CB];
-#pragma unroll
-        for (int i = 0; i < CB; i++) acc[i] = C(T(0), T(0));
-        for (int k = tid; k < M; k += NT) {
-            E t0 = th[k], f0 = fk[k];
-#pragma unroll
-            for (int i = 0; i < CB; i++) {
-                int c = c0 + i;
-                if (c < nconn) {
-                    E t = t0;
-                    int nf = cl.nflip[c];
-                    const uint8_t* s = cl.sites + c * 2 * MAXF;
-                    for (int q = 0; q < (nf & 15); q++) {
-                        int j = s[q];
-                        t += rscale(flip_delta<T>(hilb, get_bit(rb, j)), Wr[k + (int64_t)M * j]);
-                    }
-                    if (DOUBLED) for (int q = 0; q < (nf >> 4); q++) {
-                        int j = s[MAXF + q];
-                        t += rscale(flip_delta<T>(hilb, get_bit(cb, j)), Wc[k + (int64_t)M * j]);
-                    }
-                    E f, d;
-                    act_eval<ACT>(t, f, d);
-                    acc[i] += to_cx(f - f0);
-                    if (GRAD) dc[i * M + k] = d;
-                }
-            }
-        }
-        if (tid == 0) {   // visible-bias part of log psi(eta) - log psi(sigma)
-#pragma unroll
-            for (int i = 0; i < CB; i++) {
-                int c = c0 + i;
-                if (c < nconn) {
-                    int nf = cl.nflip[c];
-                    const uint8_t* s = cl.sites + c * 2 * MAXF;
-                    E lin = make_zero<E>();
-                    for (int q = 0; q < (nf & 15); q++) { int j = s[q]; lin += rscale(flip_delta<T>(hilb, get_bit(rb, j)), par[j]); }
-                    if (DOUBLED) for (int q = 0; q < (nf >> 4); q++) { int j = s[MAXF + q]; lin += rscale(flip_delta<T>(hilb, get_bit(cb, j)), par[N + j]); }
-                    acc[i] += to_cx(lin);
-                }
-            }
-        }
-        block_sum_cb<T>(acc, red);
-        C w[CB];
-#pragma unroll
-        for (int i = 0; i < CB; i++) {
-            w[i] = C(T(0), T(0));
-            if (c0 + i < nconn) { w[i] = cl.mel[c0 + i] * cx_exp(acc[i]); wtot += w[i]; }
-        }
-        if (GRAD) {
-            for (int k = tid; k < M; k += NT) {
-                C a = Ak[k];
-#pragma unroll
-                for (int i = 0; i < CB; i++) {
-                    int c = c0 + i;
-                    if (c < nconn) {
-                        C wd = w[i] * to_cx(dc[i * M + k]);
-                        a += wd;
-                        int nf = cl.nflip[c];
-                        const uint8_t* s = cl.sites + c * 2 * MAXF;
-                        for (int q = 0; q < (nf & 15); q++) { int j = s[q]; g[off_Wr + (int64_t)M * j + k] += rscale(flip_delta<T>(hilb, get_bit(rb, j)), wd); }
-                        for (int q = 0; q < (nf >> 4); q++) { int j = s[MAXF + q]; g[off_Wc + (int64_t)M * j + k] += rscale(flip_delta<T>(hilb, get_bit(cb, j)), wd); }
-                    }
-                }
-                Ak[k] = a;
-            }
-            if (tid == 0) {
-#pragma unroll
-                for (int i = 0; i < CB; i++) {
-                    int c = c0 + i;
-                    if (c < nconn) {
-                        int nf = cl.nflip[c];
-                        const uint8_t* s = cl.sites + c * 2 * MAXF;
-                        for (int q = 0; q < (nf & 15); q++) { int j = s[q]; vis[j] += rscale(flip_delta<T>(hilb, get_bit(rb, j)), w[i]); }
-                        for (int q = 0; q < (nf >> 4); q++) { int j = s[MAXF + q]; vis[N + j] += rscale(flip_delta<T>(hilb, get_bit(cb, j)), w[i]); }
-                    }
-                }
-            }
-            __syncthreads();   // dc is rewritten by the next batch
-        }
-    }
-    if (tid == 0) out_loc[b] = wtot;
-    if (GRAD) {
-        // base terms: (sum_c w_c d^c_k) v_j on every column, visible rows
-        for (int k = tid; k < M; k += NT) {
-            C a = Ak[k];
-            g[off_b + k] = a;
-            for (int j = 0; j < N; j++) {
-                g[off_Wr + (int64_t)M * j + k] += rscale(digit_value<T>(hilb, get_bit(rb, j)), a);
-                g[off_Wc + (int64_t)M * j + k] += rscale(digit_value<T>(hilb, get_bit(cb, j)), a);
-            }
-        }
-        __syncthreads();
-        for (int j = tid; j < N; j += NT) {
-            g[j] = rscale(digit_value<T>(hilb, get_bit(rb, j)), wtot) + vis[j];
-            g[N + j] = rscale(digit_value<T>(hilb, get_bit(cb, j)), wtot) + vis[N + j];
-        }
-        __syncthreads();
-        C* og = out_g + b * ld;
-        for (int64_t i = tid; i < P; i += NT) og[i] = g[i];
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// NDM (super).  items: [0,M) lambda units, [M,2M) mu units (real, each on sigma and sigma'),
-// [2M, 2M+A) ancilla units (complex pre-activation)
-// ---------------------------------------------------------------------------------------
-template <typename T, int ACT, bool GRAD>
-__global__ void local_ndm_kernel(OpDev op, const T* __restrict__ par, const uint64_t* __restrict__ prow,
-                                 const uint64_t* __restrict__ pcol, int64_t B, int N, int M, int A, int hilb,
-                                 int cap, cx<T>* __restrict__ out_loc, cx<T>* __restrict__ out_g, int64_t ld) {
-    typedef cx<T> C;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, NT = blockDim.x;
-    const int W64 = (N + 63) >> 6;
-    const int64_t b = blockIdx.x;
-    const uint64_t* rb = prow + b * W64;
-    const uint64_t* cb = pcol + b * W64;
-    const int R2 = 2 * M, NI = 2 * M + A;
-    const T half = T(0.5);
-
-    ConnList<T> cl;
-    unsigned char* p = conn_list_carve<T>(smem_raw, cap, op.n_terms, cl);
-    C* red = (C*)p; p += 32 * CB * sizeof(C);
-    T* th = (T*)p; p += align16<T>((size_t)2 * R2 * sizeof(T));      // theta (sigma) [2M], theta' [2M]
-    T* fk = (T*)p; p += align16<T>((size_t)2 * R2 * sizeof(T));
-    C* pi0 = (C*)p; p += align16<T>((size_t)A * sizeof(C));           // Pi pre-activation
-    C* fpi = (C*)p; p += align16<T>((size_t)A * sizeof(C));
-    T* dcr = (T*)p; p += align16<T>((size_t)(GRAD ? CB * 2 * R2 : 0) * sizeof(T));  // d^c (sigma | sigma')
-    C* dcp = (C*)p; p += align16<T>((size_t)(GRAD ? CB * A : 0) * sizeof(C));
-    T* dbase = (T*)p; p += align16<T>((size_t)(GRAD ? 2 * R2 : 0) * sizeof(T));
-    C* Ak = (C*)p; p += align16<T>((size_t)(GRAD ? 2 * R2 + A : 0) * sizeof(C));     // A (sigma)[2M], A'(sigma')[2M], A_pi[A]
-    C* vis = (C*)p; p += align16<T>((size_t)(GRAD ? 2 * N : 0) * sizeof(C));
-    C* g = (C*)p;
-
-    const int64_t MN = (int64_t)M * N, AN = (int64_t)A * N;
-    const int64_t o_bmu = 0, o_hmu = N, o_wmu = N + M, o_umu = o_wmu + MN, o_blam = o_umu + AN,
-                  o_hlam = o_blam + N, o_dlam = o_hlam + M, o_wlam = o_dlam + A, o_ulam = o_wlam + MN;
-    const int64_t P = o_ulam + AN;
-
-    C wdiag;
-    const int nconn = build_conn_list<T>(op, rb, cb, cl, &wdiag);
-
-    for (int it = tid; it < NI; it += NT) {
-        if (it < R2) {
-            int lay = it >= M, k = it - lay * M;
-            const T* __restrict__ w = par + (lay ? o_wmu : o_wlam) + k;
-            T t = par[(lay ? o_hmu : o_hlam) + k], tp = t;
-            for (int j = 0; j < N; j++) {
-                T wv = w[(int64_t)M * j];
-                t += wv * digit_value<T>(hilb, get_bit(rb, j));
-                tp += wv * digit_value<T>(hilb, get_bit(cb, j));
-            }
-            T f, d, fp, dp;
-            act_eval<ACT>(t, f, d);
-            act_eval<ACT>(tp, fp, dp);
-            th[it] = t; th[R2 + it] = tp; fk[it] = f; fk[R2 + it] = fp;
-            if (GRAD) { dbase[it] = d; dbase[R2 + it] = dp; Ak[it] = rscale(d, wdiag); Ak[R2 + it] = rscale(dp, wdiag); }
-        } else {
-            int a = it - R2;
-            T pr = par[o_dlam + a], pim = T(0);
-            for (int j = 0; j < N; j++) {
-                T x = digit_value<T>(hilb, get_bit(rb, j)), y = digit_value<T>(hilb, get_bit(cb, j));
-                pr += half * par[o_ulam + a + (int64_t)A * j] * (x + y);
-                pim += half * par[o_umu + a + (int64_t)A * j] * (x - y);
-            }
-            C f, d;
-            act_eval<ACT>(C(pr, pim), f, d);
-            pi0[a] = C(pr, pim); fpi[a] = f;
-            if (GRAD) Ak[2 * R2 + a] = wdiag * d;
-        }
-    }
-    if (GRAD) {
-        for (int64_t i = tid; i < P; i += NT) g[i] = C(T(0), T(0));
-        for (int i = tid; i < 2 * N; i += NT) vis[i] = C(T(0), T(0));
-    }
-    __syncthreads();
-
-    C wtot = wdiag;
-    for (int c0 = 0; c0 < nconn; c0 += CB) {
-        C acc[CB];
-#pragma unroll
-        for (int i = 0; i < CB; i++) acc[i] = C(T(0), T(0));
-        for (int it = tid; it < NI; it += NT) {
-            if (it < R2) {
-                int lay = it >= M, k = it - lay * M;
-                const T* __restrict__ w = par + (lay ? o_wmu : o_wlam) + k;
-                T t0 = th[it], tp0 = th[R2 + it], f0 = fk[it], fp0 = fk[R2 + it];
-#pragma unroll
-                for (int i = 0; i < CB; i++) {
-                    int c = c0 + i;
-                    if (c < nconn) {
-                        int nf = cl.nflip[c];
-                        const uint8_t* s = cl.sites + c * 2 * MAXF;
-                        T df = T(0), dfp = T(0);
-                        if (nf & 15) {
-                            T t = t0;
-                            for (int q = 0; q < (nf & 15); q++) { int j = s[q]; t += w[(int64_t)M * j] * flip_delta<T>(hilb, get_bit(rb, j)); }
-                            T f, d;
-                            act_eval<ACT>(t, f, d);
-                            df = f - f0;
-                            if (GRAD) dcr[i * 2 * R2 + it] = d;
-                        } else if (GRAD) dcr[i * 2 * R2 + it] = dbase[it];
-                        if (nf >> 4) {
-                            T t = tp0;
-                            for (int q = 0; q < (nf >> 4); q++) { int j = s[MAXF + q]; t += w[(int64_t)M * j] * flip_delta<T>(hilb, get_bit(cb, j)); }
-                            T f, d;
-                            act_eval<ACT>(t, f, d);
-                            dfp = f - fp0;
-                            if (GRAD) dcr[i * 2 * R2 + R2 + it] = d;
-                        } else if (GRAD) dcr[i * 2 * R2 + R2 + it] = dbase[R2 + it];
-                        if (lay == 0) acc[i].re += half * (df + dfp); else acc[i].im += half * (df - dfp);
-                    }
-                }
-            } else {
-                int a = it - R2;
-                const T* __restrict__ ul = par + o_ulam + a;
-                const T* __restrict__ um = par + o_umu + a;
-                C p0 = pi0[a], f0 = fpi[a];
-#pragma unroll
-                for (int i = 0; i < CB; i++) {
-                    int c = c0 + i;
-                    if (c < nconn) {
-                        int nf = cl.nflip[c];
-                        const uint8_t* s = cl.sites + c * 2 * MAXF;
-                        C t = p0;
-                        for (int q = 0; q < (nf & 15); q++) {
-                            int j = s[q]; T dv = half * flip_delta<T>(hilb, get_bit(rb, j));
-                            t.re += ul[(int64_t)A * j] * dv; t.im += um[(int64_t)A * j] * dv;
-                        }
-                        for (int q = 0; q < (nf >> 4); q++) {
-                            int j = s[MAXF + q]; T dv = half * flip_delta<T>(hilb, get_bit(cb, j));
-                            t.re += ul[(int64_t)A * j] * dv; t.im -= um[(int64_t)A * j] * dv;
-                        }
-                        C f, d;
-                        act_eval<ACT>(t, f, d);
-                        acc[i] += f - f0;
-                        if (GRAD) dcp[i * A + a] = d;
-                    }
-                }
-            }
-        }
-        if (tid == 0) {
-#pragma unroll
-            for (int i = 0; i < CB; i++) {
-                int c = c0 + i;
-                if (c < nconn) {
-                    int nf = cl.nflip[c];
-                    const uint8_t* s = cl.sites + c * 2 * MAXF;
-                    for (int q = 0; q < (nf & 15); q++) {
-                        int j = s[q]; T dv = half * flip_delta<T>(hilb, get_bit(rb, j));
-                        acc[i].re += par[o_blam + j] * dv; acc[i].im += par[o_bmu + j] * dv;
-                    }
-                    for (int q = 0; q < (nf >> 4); q++) {
-                        int j = s[MAXF + q]; T dv = half * flip_delta<T>(hilb, get_bit(cb, j));
-                        acc[i].re += par[o_blam + j] * dv; acc[i].im -= par[o_bmu + j] * dv;
-                    }
-                }
-            }
-        }
-        block_sum_cb<T>(acc, red);
-        C w[CB];
-#pragma unroll
-        for (int i = 0; i < CB; i++) {
-            w[i] = C(T(0), T(0));
-            if (c0 + i < nconn) { w[i] = cl.mel[c0 + i] * cx_exp(acc[i]); wtot += w[i]; }
-        }
-        if (GRAD) {
-            for (int it = tid; it < NI; it += NT) {
-                if (it < R2) {
-                    int lay = it >= M, k = it - lay * M;
-                    const int64_t ow = (lay ? o_wmu : o_wlam) + k;
-                    C a = Ak[it], ap = Ak[R2 + it];
-#pragma unroll
-                    for (int i = 0; i < CB; i++) {
-                        int c = c0 + i;
-                        if (c < nconn) {
-                            C wd = rscale(dcr[i * 2 * R2 + it], w[i]);
-                            C wdp = rscale(dcr[i * 2 * R2 + R2 + it], w[i]);
-                            a += wd; ap += wdp;
-                            int nf = cl.nflip[c];
-                            const uint8_t* s = cl.sites + c * 2 * MAXF;
-                            // lambda rows hold S = sum w d^c v^c + w d'^c v'^c; mu rows hold D = ... - ...
-                            for (int q = 0; q < (nf & 15); q++) { int j = s[q]; g[ow + (int64_t)M * j] += rscale(flip_delta<T>(hilb, get_bit(rb, j)), wd); }
-                            for (int q = 0; q < (nf >> 4); q++) {
-                                int j = s[MAXF + q];
-                                T dv = flip_delta<T>(hilb, get_bit(cb, j));
-                                g[ow + (int64_t)M * j] += rscale(lay ? -dv : dv, wdp);
-                            }
-                        }
-                    }
-                    Ak[it] = a; Ak[R2 + it] = ap;
-                } else {
-                    int a_ = it - R2;
-                    C a = Ak[2 * R2 + a_];
-#pragma unroll
-                    for (int i = 0; i < CB; i++) {
-                        int c = c0 + i;
-                        if (c < nconn) {
-                            C wd = w[i] * dcp[i * A + a_];
-                            a += wd;
-                            int nf = cl.nflip[c];
-                            const uint8_t* s = cl.sites + c * 2 * MAXF;
-                            // u_lam rows hold sum w dPi (v+v')^c, u_mu rows hold sum w dPi (v-v')^c
-                            for (int q = 0; q < (nf & 15); q++) {
-                                int j = s[q]; C x = rscale(flip_delta<T>(hilb, get_bit(rb, j)), wd);
-                                g[o_ulam + a_ + (int64_t)A * j] += x; g[o_umu + a_ + (int64_t)A * j] += x;
-                            }
-                            for (int q = 0; q < (nf >> 4); q++) {
-                                int j = s[MAXF + q]; C x = rscale(flip_delta<T>(hilb, get_bit(cb, j)), wd);
-                                g[o_ulam + a_ + (int64_t)A * j] += x; g[o_umu + a_ + (int64_t)A * j] -= x;
-                            }
-                        }
-                    }
-                    Ak[2 * R2 + a_] = a;
-                }
-            }
-            if (tid == 0) {
-#pragma unroll
-                for (int i = 0; i < CB; i++) {
-                    int c = c0 + i;
-                    if (c < nconn) {
-                        int nf = cl.nflip[c];
-                        const uint8_t* s = cl.sites + c * 2 * MAXF;
-                        for (int q = 0; q < (nf & 15); q++) { int j = s[q]; vis[j] += rscale(flip_delta<T>(hilb, get_bit(rb, j)), w[i]); }
-                        for (int q = 0; q < (nf >> 4); q++) { int j = s[MAXF + q]; vis[N + j] += rscale(flip_delta<T>(hilb, get_bit(cb, j)), w[i]); }
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    if (tid == 0) out_loc[b] = wtot;
-    if (GRAD) {
-        // finalise rows: add the base terms and apply the 1/2, i/2 prefactors
-        for (int it = tid; it < NI; it += NT) {
-            if (it < R2) {
-                int lay = it >= M, k = it - lay * M;
-                const int64_t ow = (lay ? o_wmu : o_wlam) + k;
-                C a = Ak[it], ap = Ak[R2 + it];
-                C hsum = lay ? (a - ap) : (a + ap);
-                g[(lay ? o_hmu : o_hlam) + k] = lay ? C(-half * hsum.im, half * hsum.re) : rscale(half, hsum);
-                for (int j = 0; j < N; j++) {
-                    T x = digit_value<T>(hilb, get_bit(rb, j)), y = digit_value<T>(hilb, get_bit(cb, j));
-                    C v = g[ow + (int64_t)M * j] + rscale(x, a) + rscale(lay ? -y : y, ap);
-                    g[ow + (int64_t)M * j] = lay ? C(-half * v.im, half * v.re) : rscale(half, v);
-                }
-            } else {
-                int a_ = it - R2;
-                C a = Ak[2 * R2 + a_];
-                g[o_dlam + a_] = a;
-                for (int j = 0; j < N; j++) {
-                    T x = digit_value<T>(hilb, get_bit(rb, j)), y = digit_value<T>(hilb, get_bit(cb, j));
-                    C vl = g[o_ulam + a_ + (int64_t)A * j] + rscale(x + y, a);
-                    C vm = g[o_umu + a_ + (int64_t)A * j] + rscale(x - y, a);
-                    g[o_ulam + a_ + (int64_t)A * j] = rscale(half, vl);
-                    g[o_umu + a_ + (int64_t)A * j] = C(-half * vm.im, half * vm.re);
-                }
-            }
-        }
-        for (int j = tid; j < N; j += NT) {
-            T x = digit_value<T>(hilb, get_bit(rb, j)), y = digit_value<T>(hilb, get_bit(cb, j));
-            C vl = rscale(x + y, wtot) + vis[j] + vis[N + j];
-            C vm = rscale(x - y, wtot) + vis[j] - vis[N + j];
-            g[o_blam + j] = rscale(half, vl);
-            g[o_bmu + j] = C(-half * vm.im, half * vm.re);
-        }
-        __syncthreads();
-        C* og = out_g + b * ld;
-        for (int64_t i = tid; i < P; i += NT) og[i] = g[i];
-    }
-}
-
-template <typename T>
-size_t smem_common(int cap, int n_terms) { return conn_list_bytes<T>(cap, n_terms) + 32 * CB * sizeof(cx<T>); }
-
-int round_threads(int items) {
-    int nt = ((items + 31) / 32) * 32;
-    if (nt < 64) nt = 64;
-    if (nt > 512) nt = 512;
-    return nt;
-}
-
-template <typename E, int ACT, bool DOUBLED>
-int launch_local_rbm(nq_machine_t m, nq_operator_t op, const uint64_t* pr, const uint64_t* pc, int64_t B,
-                     void* out_loc, void* out_g, int64_t ld) {
-    typedef typename elem_traits<E>::real T;
-    nq_ctx_t ctx = m->ctx;
-    const bool grad = out_g != nullptr;
-    int cap = (int)op->max_conn;
-    size_t smem = smem_common<T>(cap, op->n_terms) + 2 * align16<T>((size_t)m->M * sizeof(E)) +
-                  align16<T>((size_t)CB * m->M * sizeof(E));
-    if (grad) smem += align16<T>((size_t)m->M * sizeof(cx<T>)) + align16<T>((size_t)2 * m->N * sizeof(cx<T>)) +
-                      (size_t)m->P * sizeof(cx<T>);
-    if (smem > ctx->smem_optin)
-        return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "local estimator needs %zu B shared memory per CTA (limit %zu)", smem, ctx->smem_optin);
-    int nt = round_threads(m->M);
-    if (grad) {
-        if (!DOUBLED) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "gradient estimator is defined for Liouvillians only");
-        auto kern = local_rbm_kernel<E, ACT, DOUBLED, DOUBLED>;
-        NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NQ_LAUNCH(ctx, kern, (unsigned)B, nt, smem, op_dev(op), (const E*)m->params, pr, pc, B, m->N, m->M, (int)m->hilb, cap, (cx<T>*)out_loc, (cx<T>*)out_g, ld);
-    } else {
-        auto kern = local_rbm_kernel<E, ACT, DOUBLED, false>;
-        NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NQ_LAUNCH(ctx, kern, (unsigned)B, nt, smem, op_dev(op), (const E*)m->params, pr, pc, B, m->N, m->M, (int)m->hilb, cap, (cx<T>*)out_loc, (cx<T>*)nullptr, ld);
-    }
-    return NQ_OK;
-}
-
-template <typename T, int ACT>
-int launch_local_ndm(nq_machine_t m, nq_operator_t op, const uint64_t* pr, const uint64_t* pc, int64_t B,
-                     void* out_loc, void* out_g, int64_t ld) {
-    nq_ctx_t ctx = m->ctx;
-    const bool grad = out_g != nullptr;
-    int cap = (int)op->max_conn;
-    const int R2 = 2 * m->M, A = m->A;
-    size_t smem = smem_common<T>(cap, op->n_terms) + 2 * align16<T>((size_t)2 * R2 * sizeof(T)) +
-                  2 * align16<T>((size_t)A * sizeof(cx<T>));
-    if (grad) smem += align16<T>((size_t)CB * 2 * R2 * sizeof(T)) + align16<T>((size_t)CB * A * sizeof(cx<T>)) +
-                      align16<T>((size_t)2 * R2 * sizeof(T)) + align16<T>((size_t)(2 * R2 + A) * sizeof(cx<T>)) +
-                      align16<T>((size_t)2 * m->N * sizeof(cx<T>)) + (size_t)m->P * sizeof(cx<T>);
-    if (smem > ctx->smem_optin)
-        return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "local estimator needs %zu B shared memory per CTA (limit %zu)", smem, ctx->smem_optin);
-    int nt = round_threads(R2 + A);
-    if (grad) {
-        auto kern = local_ndm_kernel<T, ACT, true>;
-        NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NQ_LAUNCH(ctx, kern, (unsigned)B, nt, smem, op_dev(op), (const T*)m->params, pr, pc, B, m->N, m->M, A, (int)m->hilb, cap, (cx<T>*)out_loc, (cx<T>*)out_g, ld);
-    } else {
-        auto kern = local_ndm_kernel<T, ACT, false>;
-        NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NQ_LAUNCH(ctx, kern, (unsigned)B, nt, smem, op_dev(op), (const T*)m->params, pr, pc, B, m->N, m->M, A, (int)m->hilb, cap, (cx<T>*)out_loc, (cx<T>*)nullptr, ld);
-    }
-    return NQ_OK;
-}
-
-template <typename E>
-int dispatch_local_rbm(nq_machine_t m, nq_operator_t op, const uint64_t* pr, const uint64_t* pc, int64_t B,
-                       void* out_loc, void* out_g, int64_t ld) {
-    if (m->kind == NQ_RBMSPLIT) return launch_local_rbm<E, NQ_SOFTPLUS, true>(m, op, pr, pc, B, out_loc, out_g, ld);
-    if (m->act == NQ_SOFTPLUS) return launch_local_rbm<E, NQ_SOFTPLUS, false>(m, op, pr, pc, B, out_loc, out_g, ld);
-    return launch_local_rbm<E, NQ_LOGCOSH, false>(m, op, pr, pc, B, out_loc, out_g, ld);
-}
+#include "nq_estimators.inc"
 
 }  // namespace
 
@@ -809,8 +290,31 @@ extern "C" int nq_operator_create(nq_ctx_t ctx, nq_space space, int N, int n_par
         if (L >= n_parts || R >= n_parts || (L < 0 && R < 0)) return nq_fail(ctx, NQ_ERR_SHAPE, "term %d references no valid part", t);
         max_conn += (L >= 0 ? max_row[L] : 1) * (R >= 0 ? max_row[R] : 1);
     }
+    // site_local: every connection flips at most ONE site index (the same on sigma and sigma'), so the
+    // estimator kernels can deal connections to warps by site without write conflicts
+    int site_local = 1;
+    {
+        std::vector<uint32_t> part_mask(n_parts, 0u);
+        for (int p = 0; p < n_parts; p++)
+            for (int64_t e = row_ptr[row0[p]]; e < row_ptr[row0[p] + ((int64_t)1 << part_nsites[p])]; e++) part_mask[p] |= entry_flip[e];
+        for (int t = 0; t < n_terms && site_local; t++) {
+            int parts[2] = {term_left[t], space == NQ_SUPER ? term_right[t] : -1};
+            int site = -1;
+            for (int q = 0; q < 2; q++) {
+                int p = parts[q];
+                if (p < 0) continue;
+                for (int i = 0; i < part_nsites[p]; i++)
+                    if ((part_mask[p] >> i) & 1u) {
+                        int sidx = part_sites[site_ptr[p] + i];
+                        if (site >= 0 && site != sidx) site_local = 0;
+                        site = sidx;
+                    }
+            }
+        }
+    }
     nq_operator_t op = new nq_operator_s();
     memset(op, 0, sizeof(*op));
+    op->site_local = site_local;
     op->ctx = ctx; op->space = space; op->N = N; op->n_parts = n_parts; op->n_terms = n_terms;
     op->n_rows = rows; op->n_entries = n_entries; op->max_conn = max_conn > 0 ? max_conn : 1; op->max_part_sites = maxk;
     std::vector<int32_t> tr(n_terms, -1);

@@ -109,3 +109,45 @@ def test_estimator_argument_errors(nq, ctx):
     _, pH5 = H.p_tfim_1d(nq, 5)
     with pytest.raises(nq.NQError):            # site-count mismatch
         nq.local_scalar(rbm, pH5.to_device(ctx), S)
+
+
+def _xx_models(nq, N, fock):
+    """XX + Z chain with sigma^- jumps: connections flip TWO sites (generic, non site-local path)."""
+    from oracle import operators as OO
+    from oracle.hilbert import HomogeneousFock, HomogeneousSpin
+    oh = HomogeneousFock(N) if fock else HomogeneousSpin(N)
+    ph = nq.HomogeneousFock(N) if fock else nq.HomogeneousSpin(N)
+    oHm, pHm, oj, pj = None, nq.LocalOperator(ph), [], []
+    for i in range(1, N):
+        oHm = OO.add(oHm, OO.mul(OO.scale(0.7, OO.sigmax(oh, i)), OO.sigmax(oh, i + 1)))
+        pHm = pHm + (0.7 * nq.sigmax(ph, i)) * nq.sigmax(ph, i + 1)
+    for i in range(1, N + 1):
+        oHm = OO.add(oHm, OO.scale(0.3, OO.sigmaz(oh, i)))
+        pHm = pHm + 0.3 * nq.sigmaz(ph, i)
+        oHm = OO.add(oHm, OO.scale(0.2, OO.sigmay(oh, i)))
+        pHm = pHm + 0.2 * nq.sigmay(ph, i)
+        oj.append(OO.sigmam(oh, i))
+        pj.append(nq.sigmam(ph, i))
+    return oh, oHm, OO.liouvillian(oHm, oj), ph, pHm, nq.liouvillian(pHm, pj)
+
+
+def test_generic_two_site_flips(nq, ctx):
+    N = 6
+    oh, oHm, ol, ph, pHm, pl = _xx_models(nq, N, fock=False)
+    # ket
+    om, pm, _ = H.make_pair(nq, ctx, "rbm", "spin", N, 2, np.complex128, OM.LOGCOSH)
+    S = H.rand_states("spin", N, 25, 3)
+    dH = pHm.to_device(ctx)
+    counts, mels, fr, _ = dH.connections(S)
+    for b in range(5):
+        ref = OE.connection_list_ket(oHm, S[:, b])
+        assert [(complex(mels[b, c]), _mask(fr[b, c])) for c in range(counts[b])] == ref
+    H.assert_close(nq.local_scalar(pm, dH, S), OE.local_scalar_ket(om, oHm, S), 1e-11, "E_loc XX")
+    # Liouvillian with gradient (shared-memory atomics path)
+    for kind, dtype in (("ndm", np.float64), ("rbmsplit", np.complex128)):
+        om, pm, _ = H.make_pair(nq, ctx, kind, "spin", N, 2, dtype, OM.SOFTPLUS)
+        R, Cc = H.rand_states("spin", N, 11, 41), H.rand_states("spin", N, 11, 42)
+        ref_l, ref_g = OE.local_grad_super(om, ol, R, Cc)
+        loc, g = nq.local_grad(pm, pl.to_device(ctx), (R, Cc))
+        H.assert_close(loc, ref_l, 1e-11, "L_loc XX " + kind)
+        H.assert_close(g, ref_g, 1e-11, "grad L_loc XX " + kind)
