@@ -264,6 +264,59 @@ template <int ACT, typename E> __device__ __forceinline__ void act_eval(E x, E& 
 }
 
 // --------------------------------------------------------------------------------------
+// flip-ratio algebra.  With s = f'(theta) cached for the sampled configuration and Ep = exp(+Delta),
+// Em = exp(-Delta) for the change Delta of the pre-activation under a flip,
+//   softplus: (1+e^{theta+Delta})/(1+e^theta) = 1 + s (Ep - 1),         s' = s Ep / factor
+//   logcosh : cosh(theta+Delta)/cosh(theta)   = (Ep (1+t) + Em (1-t))/2, t' = (Ep(1+t) - Em(1-t)) / (2 factor)
+// so a connected configuration costs a handful of multiply-adds and one division per hidden unit and
+// NO transcendental (Ep, Em come from the per-parameter tables built by nq_machine_ensure_tables).
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ float e_exp(float x) { return expf(x); }
+__device__ __forceinline__ double e_exp(double x) { return exp(x); }
+template <typename T> __device__ __forceinline__ cx<T> e_exp(cx<T> x) { return cx_exp(x); }
+template <typename T> NQ_HD cx<T> cx_div(cx<T> a, cx<T> b) {
+    T inv = T(1) / (b.re * b.re + b.im * b.im);
+    return cx<T>((a.re * b.re + a.im * b.im) * inv, (a.im * b.re - a.re * b.im) * inv);
+}
+NQ_HD float e_div(float a, float b) { return a / b; }
+NQ_HD double e_div(double a, double b) { return a / b; }
+template <typename T> NQ_HD cx<T> e_div(cx<T> a, cx<T> b) { return cx_div(a, b); }
+NQ_HD float e_mul(float a, float b) { return a * b; }
+NQ_HD double e_mul(double a, double b) { return a * b; }
+template <typename T> NQ_HD cx<T> e_mul(cx<T> a, cx<T> b) { return a * b; }
+template <typename E> NQ_HD E e_one() { return from_real<E, typename elem_traits<E>::real>(typename elem_traits<E>::real(1)); }
+template <int ACT, typename E>
+__device__ __forceinline__ void ratio_step(E s, E Ep, E Em, E& fac, E& snew) {
+    typedef typename elem_traits<E>::real T;
+    if (ACT == NQ_SOFTPLUS) {
+        fac = e_one<E>() + e_mul(s, Ep - e_one<E>());
+        snew = e_div(e_mul(s, Ep), fac);
+    } else {
+        E a = e_mul(Ep, e_one<E>() + s), b = e_mul(Em, e_one<E>() - s);
+        E sum = a + b;
+        fac = rscale(T(0.5), sum);
+        snew = e_div(a - b, sum);
+    }
+}
+// products are accumulated in double precision whatever the mode
+NQ_HD double to_d(float a) { return (double)a; }
+NQ_HD double to_d(double a) { return a; }
+template <typename T> NQ_HD cxd to_d(cx<T> a) { return cxd((double)a.re, (double)a.im); }
+__device__ __forceinline__ double warp_prod(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+__device__ __forceinline__ cxd warp_prod(cxd v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        cxd o(__shfl_xor_sync(0xffffffffu, v.re, m), __shfl_xor_sync(0xffffffffu, v.im, m));
+        v = v * o;
+    }
+    return v;
+}
+
+// --------------------------------------------------------------------------------------
 // warp / block reductions
 // --------------------------------------------------------------------------------------
 __device__ __forceinline__ float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }

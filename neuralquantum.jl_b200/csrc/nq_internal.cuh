@@ -19,6 +19,10 @@ struct nq_machine_s {
     nq_dtype out_dtype;   // log psi / gradient dtype
     int64_t P;
     void* params;         // device, P elements of dtype
+    // single-flip ratio tables exp(+-c W) (c = |change of a site value|), rebuilt lazily after every
+    // parameter change; see nq_machine_ensure_tables (nq_machines.cu)
+    void* etab;
+    bool etab_valid;
     bool doubled() const { return kind != NQ_RBM; }
 };
 
@@ -46,6 +50,7 @@ struct nq_operator_s {
 // device-pointer internals shared between translation units
 int nq_pack_device(nq_ctx_t ctx, nq_hilbert h, int N, int64_t B, const void* dsigma, nq_dtype sdtype, uint64_t* dpacked);
 int nq_unpack_device(nq_ctx_t ctx, nq_hilbert h, int N, int64_t B, const uint64_t* dpacked, void* dsigma, nq_dtype sdtype);
+int nq_machine_ensure_tables(nq_machine_t m);
 int nq_machine_eval_device(nq_machine_t m, const uint64_t* prow, const uint64_t* pcol, int64_t B,
                            void* out, void* O, int64_t ldO);
 struct NqStage;

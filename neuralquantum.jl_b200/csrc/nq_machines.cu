@@ -313,6 +313,34 @@ ndm_evalgrad_kernel(const T* __restrict__ par, const uint64_t* __restrict__ prow
     block_reduce_store<C, TB, NT>(lsum, red, out, s0, nb);
 }
 
+// exp(+-c W) tables: out[sign][i] = exp((sign ? -c : c) * w[i])
+template <typename E>
+__global__ void etab_kernel(const E* __restrict__ w, E* __restrict__ out, int64_t n, typename elem_traits<E>::real c) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    E x = rscale(c, w[i]);
+    out[i] = e_exp(x);
+    out[n + i] = e_exp(-x);
+}
+// NDM ancilla tables: out[sign][a + A j] = exp(+-(c/2) (u_lam + i u_mu))
+template <typename T>
+__global__ void etab_pi_kernel(const T* __restrict__ ul, const T* __restrict__ um, cx<T>* __restrict__ out, int64_t n, T c) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cx<T> x(T(0.5) * c * ul[i], T(0.5) * c * um[i]);
+    out[i] = cx_exp(x);
+    out[n + i] = cx_exp(-x);
+}
+
+template <typename T>
+__global__ void etab_strided_kernel(const T* __restrict__ w, T* __restrict__ out, int64_t n, int64_t sign_stride, T c) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T x = c * w[i];
+    out[i] = m_exp(x);
+    out[sign_stride + i] = m_exp(-x);
+}
+
 template <typename E>
 __global__ void log_prob_kernel(const E* __restrict__ in, typename elem_traits<E>::real* __restrict__ out, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -385,6 +413,65 @@ int nq_machine_eval_device(nq_machine_t m, const uint64_t* prow, const uint64_t*
     }
 }
 
+// Layouts.  RBM/RBMSplit (element E): etab[sign][mat][k + M j], mat 0 = W / Wr, 1 = Wc.
+// NDM (real T): etab[sign][lay][k + M j], lay 0 = w_lam, 1 = w_mu, followed (16-byte aligned) by the complex
+// ancilla table [sign][a + A j].  sign 0: the site value increases, 1: it decreases.
+static size_t etab_bytes(nq_machine_t m) {
+    const int64_t MN = (int64_t)m->M * m->N, AN = (int64_t)m->A * m->N;
+    const size_t es = nq_dtype_size(m->dtype);
+    if (m->kind == NQ_NDM) return ((size_t)4 * MN * es + 15) / 16 * 16 + (size_t)2 * AN * 2 * es;
+    return (size_t)2 * (m->kind == NQ_RBMSPLIT ? 2 : 1) * MN * es;
+}
+
+template <typename E>
+static int build_tables_rbm(nq_machine_t m) {
+    typedef typename elem_traits<E>::real T;
+    nq_ctx_t ctx = m->ctx;
+    const int64_t MN = (int64_t)m->M * m->N;
+    const int nmat = m->kind == NQ_RBMSPLIT ? 2 : 1;
+    const int64_t n = nmat * MN;       // Wr and Wc are contiguous in the parameter vector
+    const E* W = (const E*)m->params + (m->kind == NQ_RBMSPLIT ? 2 * m->N : m->N) + m->M;
+    T c = m->hilb == NQ_SPIN ? T(2) : T(1);
+    NQ_LAUNCH(ctx, etab_kernel<E>, (unsigned)((n + 255) / 256), 256, 0, W, (E*)m->etab, n, c);
+    return NQ_OK;
+}
+
+template <typename T>
+static int build_tables_ndm(nq_machine_t m) {
+    nq_ctx_t ctx = m->ctx;
+    const int64_t N = m->N, M = m->M, A = m->A, MN = M * N, AN = A * N;
+    const T* par = (const T*)m->params;
+    const int64_t o_wmu = N + M, o_umu = o_wmu + MN, o_wlam = o_umu + AN + N + M + A, o_ulam = o_wlam + MN;
+    T c = m->hilb == NQ_SPIN ? T(2) : T(1);
+    T* tr = (T*)m->etab;
+    // [sign][lay][MN]: write lam and mu with sign-major layout through two launches of n = MN each
+    unsigned g = (unsigned)((MN + 255) / 256);
+    // etab_kernel writes out[i] (sign 0) and out[n+i] (sign 1) with n = stride between signs = 2 MN
+    NQ_LAUNCH(ctx, etab_strided_kernel<T>, g, 256, 0, par + o_wlam, tr, MN, (int64_t)2 * MN, c);
+    NQ_LAUNCH(ctx, etab_strided_kernel<T>, g, 256, 0, par + o_wmu, tr + MN, MN, (int64_t)2 * MN, c);
+    cx<T>* tc = (cx<T>*)((char*)m->etab + ((size_t)4 * MN * sizeof(T) + 15) / 16 * 16);
+    NQ_LAUNCH(ctx, etab_pi_kernel<T>, (unsigned)((AN + 255) / 256), 256, 0, par + o_ulam, par + o_umu, tc, AN, c);
+    return NQ_OK;
+}
+
+int nq_machine_ensure_tables(nq_machine_t m) {
+    if (m->etab_valid) return NQ_OK;
+    nq_ctx_t ctx = m->ctx;
+    if (!m->etab) {
+        if (cudaMalloc(&m->etab, etab_bytes(m)) != cudaSuccess) { cudaGetLastError(); return nq_fail(ctx, NQ_ERR_ALLOC, "ratio table allocation failed"); }
+    }
+    int s;
+    if (m->kind == NQ_NDM) s = m->dtype == NQ_F64 ? build_tables_ndm<double>(m) : build_tables_ndm<float>(m);
+    else switch (m->dtype) {
+        case NQ_F32: s = build_tables_rbm<float>(m); break;
+        case NQ_F64: s = build_tables_rbm<double>(m); break;
+        case NQ_C64: s = build_tables_rbm<cxf>(m); break;
+        default: s = build_tables_rbm<cxd>(m); break;
+    }
+    if (s == NQ_OK) m->etab_valid = true;
+    return s;
+}
+
 // ---------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------
@@ -402,6 +489,7 @@ extern "C" int nq_machine_create(nq_ctx_t ctx, nq_machine_kind kind, nq_hilbert 
     m->ctx = ctx; m->kind = kind; m->hilb = h; m->N = N; m->M = M; m->A = A;
     m->act = kind == NQ_RBMSPLIT ? NQ_SOFTPLUS : act;
     m->dtype = dtype;
+    m->etab = nullptr; m->etab_valid = false;
     m->out_dtype = kind == NQ_NDM ? nq_complex_of(dtype) : dtype;
     int64_t MN = (int64_t)M * N;
     m->P = kind == NQ_RBM ? N + M + MN : kind == NQ_RBMSPLIT ? 2 * N + M + 2 * MN
@@ -421,6 +509,7 @@ extern "C" int nq_machine_destroy(nq_machine_t m) {
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     cudaFree(m->params);
+    cudaFree(m->etab);
     delete m;
     return NQ_OK;
 }
@@ -442,6 +531,7 @@ extern "C" int nq_machine_set_params(nq_machine_t m, const void* params, int64_t
     if (P != m->P) return nq_fail(m->ctx, NQ_ERR_SHAPE, "expected %lld parameters, got %lld", (long long)m->P, (long long)P);
     NQ_CUDA(m->ctx, cudaSetDevice(m->ctx->device));
     NQ_CUDA(m->ctx, cudaMemcpyAsync(m->params, params, (size_t)P * nq_dtype_size(m->dtype), cudaMemcpyDefault, m->ctx->stream));
+    m->etab_valid = false;
     if (!nq_is_device_ptr(params)) NQ_CUDA(m->ctx, cudaStreamSynchronize(m->ctx->stream));
     return NQ_OK;
 }

@@ -215,6 +215,7 @@ int nq_local_device(nq_machine_t m, nq_operator_t op, const uint64_t* pr, const 
     if (op->max_part_sites > MAXF) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "local terms on more than %d sites", MAXF);
     if (m->N > 256) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "estimator kernels index sites with 8 bits (N <= 256)");
     if (B == 0) return NQ_OK;
+    NQ_CHECK(nq_machine_ensure_tables(m));
     if (m->kind == NQ_NDM) {
         if (m->dtype == NQ_F64)
             return m->act == NQ_SOFTPLUS ? launch_local_ndm<double, NQ_SOFTPLUS>(m, op, pr, pc, B, out_loc, out_g, ld)

@@ -103,22 +103,27 @@ __device__ __forceinline__ void draw(const RunArgs& a, int64_t chain, uint64_t p
 }
 
 // ---- RBM / RBMSplit -------------------------------------------------------------------
+// Per chain (warp) only s_k = f'(theta_k) is tracked: with the per-parameter tables Ep = exp(+-c W_kj) a
+// proposal costs one table load, a few multiply-adds and one division per hidden unit -- no transcendental --
+//   psi(eta)/psi(sigma) = e^{a_j dv} prod_k [1 + s_k (Ep - 1)]      (softplus; see ratio_step for logcosh)
+// and an accepted move updates s_k in place.  s is recomputed from the configuration once per stored sample.
 template <typename E, int ACT, bool DOUBLED>
-__global__ void sampler_rbm_kernel(const E* __restrict__ par, uint64_t* __restrict__ st_row, uint64_t* __restrict__ st_col,
-                                   RunArgs a) {
+__global__ void sampler_rbm_kernel(const E* __restrict__ par, const E* __restrict__ tab, uint64_t* __restrict__ st_row,
+                                   uint64_t* __restrict__ st_col, RunArgs a) {
     typedef typename elem_traits<E>::real T;
+    typedef decltype(to_d(E())) PD;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int64_t chain = blockIdx.x * (int64_t)wpb + warp;
     if (chain >= a.B) return;
     const int N = a.N, M = a.M, W64 = (N + 63) >> 6;
-    E* th = (E*)smem_raw + (size_t)warp * 4 * M;
-    E* fk = th + M;
-    E* tth = fk + M;
-    E* tf = tth + M;
+    E* sk = (E*)smem_raw + (size_t)warp * 2 * M;
+    E* ts = sk + M;
     const int64_t off_b = DOUBLED ? 2 * N : N;
     const E* __restrict__ Wr = par + off_b + M;
     const E* __restrict__ Wc = Wr + (int64_t)M * N;
+    const int64_t MN = (int64_t)M * N;
+    const int nmat = DOUBLED ? 2 : 1;
     uint64_t rb[MAXW], cb[MAXW];
 #pragma unroll
     for (int w = 0; w < MAXW; w++) {
@@ -129,7 +134,6 @@ __global__ void sampler_rbm_kernel(const E* __restrict__ par, uint64_t* __restri
     unsigned nacc = 0;
     const int nsteps = a.burn + a.L;
     for (int step = 0; step < nsteps; step++) {
-        // refresh theta from the configuration (bounds incremental round-off drift)
         for (int k = lane; k < M; k += 32) {
             E t = par[off_b + k];
             for (int j = 0; j < N; j++) {
@@ -138,9 +142,10 @@ __global__ void sampler_rbm_kernel(const E* __restrict__ par, uint64_t* __restri
             }
             E f, d;
             act_eval<ACT>(t, f, d);
-            th[k] = t; fk[k] = f;
+            sk[k] = d;
         }
         __syncwarp();
+#pragma unroll 1
         for (int ps = 0; ps < a.passes; ps++) {
             int pic = step * a.passes + ps;
             int site; T u;
@@ -148,21 +153,23 @@ __global__ void sampler_rbm_kernel(const E* __restrict__ par, uint64_t* __restri
             const bool col = DOUBLED && site >= N;
             const int j = col ? site - N : site;
             const T dv = flip_delta<T>(a.hilb, get_bit(col ? cb : rb, j));
-            const E* __restrict__ wj = (col ? Wc : Wr) + (int64_t)M * j;
-            E part = make_zero<E>();
+            const int sg = dv > T(0) ? 0 : 1, mat = col ? 1 : 0;
+            const E* __restrict__ tp = tab + (int64_t)(sg * nmat + mat) * MN + (int64_t)M * j;
+            const E* __restrict__ tm = tab + (int64_t)((1 - sg) * nmat + mat) * MN + (int64_t)M * j;
+            PD prod = to_d(e_one<E>());
             for (int k = lane; k < M; k += 32) {
-                E t = th[k] + rscale(dv, wj[k]);
-                E f, d;
-                act_eval<ACT>(t, f, d);
-                part += f - fk[k];
-                tth[k] = t; tf[k] = f;
+                E Ep = tp[k], Em = ACT == NQ_LOGCOSH ? tm[k] : e_one<E>();
+                E fac, sn;
+                ratio_step<ACT>(sk[k], Ep, Em, fac, sn);
+                prod = prod * to_d(fac);
+                ts[k] = sn;
             }
-            part = warp_sum(part);
-            part += rscale(dv, par[(col ? N : 0) + j]);
-            const T dlp = T(2) * real_part(part);
-            const bool acc = (u - m_exp(dlp)) < T(0);
+            prod = warp_prod(prod);
+            const PD ratio = prod * to_d(e_exp(rscale(dv, par[(col ? N : 0) + j])));
+            const double pr = to_d(real_part(ratio)) * to_d(real_part(ratio)) + to_d(imag_part(ratio)) * to_d(imag_part(ratio));
+            const bool acc = (u - (T)pr) < T(0);
             if (acc) {
-                for (int k = lane; k < M; k += 32) { th[k] = tth[k]; fk[k] = tf[k]; }
+                for (int k = lane; k < M; k += 32) sk[k] = ts[k];
                 if (col) cb[j >> 6] ^= 1ull << (j & 63); else rb[j >> 6] ^= 1ull << (j & 63);
                 nacc++;
             }
@@ -181,28 +188,24 @@ __global__ void sampler_rbm_kernel(const E* __restrict__ par, uint64_t* __restri
 }
 
 // ---- NDM ------------------------------------------------------------------------------
-// log p = 2 Re log rho = 2 [Gamma_lambda + Re sum_a f(Pi_a)]: the mu hidden layer only enters the
-// phase, so the sampler tracks the lambda layer (on sigma and sigma') and the ancilla layer only.
-// per warp: Pi[A], fPi[A], tentative Pi/fPi [A] (complex); th[2M] (side*M + k), f[2M], tentative th/f [M]
+// p(sigma,sigma') = |rho|^2: the mu hidden layer only enters the phase, so the chain tracks the lambda layer
+// (on sigma and sigma') and the ancilla layer:  |rho(eta)/rho(sigma)|^2 = e^{b_lam_j dv} prod_lambda |prod_Pi|^2.
+// per warp: spi[A], tspi[A] (complex); sl[2M] (side*M + k), tsl[M]
 template <typename T, int ACT>
-__global__ void sampler_ndm_kernel(const T* __restrict__ par, uint64_t* __restrict__ st_row, uint64_t* __restrict__ st_col,
-                                   RunArgs a) {
+__global__ void sampler_ndm_kernel(const T* __restrict__ par, const T* __restrict__ tabr, const cx<T>* __restrict__ tabc,
+                                   uint64_t* __restrict__ st_row, uint64_t* __restrict__ st_col, RunArgs a) {
     typedef cx<T> C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int64_t chain = blockIdx.x * (int64_t)wpb + warp;
     if (chain >= a.B) return;
     const int N = a.N, M = a.M, A = a.A, W64 = (N + 63) >> 6;
-    const size_t per_warp = (size_t)(6 * M) * sizeof(T) + (size_t)(4 * A) * sizeof(C);
-    unsigned char* base = smem_raw + (size_t)warp * per_warp;
-    C* pi0 = (C*)base;            // [A]
-    C* fpi = pi0 + A;
-    C* tpi = fpi + A;
-    C* tfpi = tpi + A;
-    T* th = (T*)(tfpi + A);       // [2M]
-    T* fk = th + 2 * M;           // [2M]
-    T* tth = fk + 2 * M;          // [M]
-    T* tf = tth + M;              // [M]
+    const size_t per_warp = (size_t)(3 * M) * sizeof(T) + (size_t)(2 * A) * sizeof(C);
+    unsigned char* base = smem_raw + (size_t)warp * ((per_warp + 15) / 16 * 16);
+    C* spi = (C*)base;            // [A]
+    C* tspi = spi + A;
+    T* sl = (T*)(tspi + A);       // [2M]
+    T* tsl = sl + 2 * M;          // [M]
     const int64_t MN = (int64_t)M * N, AN = (int64_t)A * N;
     const int64_t o_wmu = N + M, o_umu = o_wmu + MN, o_blam = o_umu + AN,
                   o_hlam = o_blam + N, o_dlam = o_hlam + M, o_wlam = o_dlam + A, o_ulam = o_wlam + MN;
@@ -227,7 +230,7 @@ __global__ void sampler_ndm_kernel(const T* __restrict__ par, uint64_t* __restri
             T f, d, fp, dp;
             act_eval<ACT>(t, f, d);
             act_eval<ACT>(tp, fp, dp);
-            th[k] = t; fk[k] = f; th[M + k] = tp; fk[M + k] = fp;
+            sl[k] = d; sl[M + k] = dp;
         }
         for (int q = lane; q < A; q += 32) {
             T pr = par[o_dlam + q], pim = T(0);
@@ -238,9 +241,10 @@ __global__ void sampler_ndm_kernel(const T* __restrict__ par, uint64_t* __restri
             }
             C f, d;
             act_eval<ACT>(C(pr, pim), f, d);
-            pi0[q] = C(pr, pim); fpi[q] = f;
+            spi[q] = d;
         }
         __syncwarp();
+#pragma unroll 1
         for (int ps = 0; ps < a.passes; ps++) {
             int pic = step * a.passes + ps;
             int site; T u;
@@ -248,32 +252,36 @@ __global__ void sampler_ndm_kernel(const T* __restrict__ par, uint64_t* __restri
             const bool col = site >= N;
             const int j = col ? site - N : site;
             const T dv = flip_delta<T>(a.hilb, get_bit(col ? cb : rb, j));
+            const int sg = dv > T(0) ? 0 : 1;
             const int so = col ? M : 0;
-            T part = T(0);
+            const T* __restrict__ tp = tabr + (int64_t)sg * 2 * MN + (int64_t)M * j;          // lambda layer = lay 0
+            const T* __restrict__ tm = tabr + (int64_t)(1 - sg) * 2 * MN + (int64_t)M * j;
+            const C* __restrict__ cp = tabc + (int64_t)sg * AN + (int64_t)A * j;
+            const C* __restrict__ cm = tabc + (int64_t)(1 - sg) * AN + (int64_t)A * j;
+            double pl = 1.0;
+            cxd pp(1.0, 0.0);
             for (int k = lane; k < M; k += 32) {
-                T t = th[so + k] + dv * par[o_wlam + k + (int64_t)M * j];
-                T f, d;
-                act_eval<ACT>(t, f, d);
-                part += half * (f - fk[so + k]);
-                tth[k] = t; tf[k] = f;
+                T Ep = tp[k], Em = ACT == NQ_LOGCOSH ? tm[k] : T(1);
+                T fac, sn;
+                ratio_step<ACT>(sl[so + k], Ep, Em, fac, sn);
+                pl *= (double)fac;
+                tsl[k] = sn;
             }
             for (int q = lane; q < A; q += 32) {
-                C t = pi0[q];
-                T hd = half * dv;
-                t.re += hd * par[o_ulam + q + (int64_t)A * j];
-                t.im += (col ? -hd : hd) * par[o_umu + q + (int64_t)A * j];
-                C f, d;
-                act_eval<ACT>(t, f, d);
-                part += f.re - fpi[q].re;
-                tpi[q] = t; tfpi[q] = f;
+                C Ep = cp[q], Em = ACT == NQ_LOGCOSH ? cm[q] : C(T(1), T(0));
+                if (col) { Ep.im = -Ep.im; Em.im = -Em.im; }
+                C fac, sn;
+                ratio_step<ACT>(spi[q], Ep, Em, fac, sn);
+                pp = pp * to_d(fac);
+                tspi[q] = sn;
             }
-            part = warp_sum(part);
-            part += half * dv * par[o_blam + j];
-            const T dlp = T(2) * part;
-            const bool acc = (u - m_exp(dlp)) < T(0);
+            pl = warp_prod(pl);
+            pp = warp_prod(pp);
+            const double pr = pl * exp((double)(dv * par[o_blam + j])) * (pp.re * pp.re + pp.im * pp.im);
+            const bool acc = (u - (T)pr) < T(0);
             if (acc) {
-                for (int k = lane; k < M; k += 32) { th[so + k] = tth[k]; fk[so + k] = tf[k]; }
-                for (int q = lane; q < A; q += 32) { pi0[q] = tpi[q]; fpi[q] = tfpi[q]; }
+                for (int k = lane; k < M; k += 32) sl[so + k] = tsl[k];
+                for (int q = lane; q < A; q += 32) spi[q] = tspi[q];
                 if (col) cb[j >> 6] ^= 1ull << (j & 63); else rb[j >> 6] ^= 1ull << (j & 63);
                 nacc++;
             }
@@ -295,7 +303,7 @@ template <typename E, int ACT, bool DOUBLED>
 int launch_sampler_rbm(nq_sampler_t s, const RunArgs& a) {
     nq_machine_t m = s->m;
     nq_ctx_t ctx = m->ctx;
-    size_t per_warp = (size_t)4 * m->M * sizeof(E);
+    size_t per_warp = (size_t)2 * m->M * sizeof(E);
     int wpb = 8;
     while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
     size_t smem = per_warp * wpb;
@@ -303,7 +311,7 @@ int launch_sampler_rbm(nq_sampler_t s, const RunArgs& a) {
     auto kern = sampler_rbm_kernel<E, ACT, DOUBLED>;
     NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((s->B + wpb - 1) / wpb);
-    NQ_LAUNCH(ctx, kern, grid, wpb * 32, smem, (const E*)m->params, s->prow, s->pcol, a);
+    NQ_LAUNCH(ctx, kern, grid, wpb * 32, smem, (const E*)m->params, (const E*)m->etab, s->prow, s->pcol, a);
     return NQ_OK;
 }
 
@@ -311,7 +319,8 @@ template <typename T, int ACT>
 int launch_sampler_ndm(nq_sampler_t s, const RunArgs& a) {
     nq_machine_t m = s->m;
     nq_ctx_t ctx = m->ctx;
-    size_t per_warp = (size_t)6 * m->M * sizeof(T) + (size_t)4 * m->A * sizeof(cx<T>);
+    size_t per_warp = ((size_t)3 * m->M * sizeof(T) + (size_t)2 * m->A * sizeof(cx<T>) + 15) / 16 * 16;
+    const cx<T>* tabc = (const cx<T>*)((const char*)m->etab + ((size_t)4 * m->M * m->N * sizeof(T) + 15) / 16 * 16);
     int wpb = 8;
     while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
     size_t smem = per_warp * wpb;
@@ -319,7 +328,7 @@ int launch_sampler_ndm(nq_sampler_t s, const RunArgs& a) {
     auto kern = sampler_ndm_kernel<T, ACT>;
     NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((s->B + wpb - 1) / wpb);
-    NQ_LAUNCH(ctx, kern, grid, wpb * 32, smem, (const T*)m->params, s->prow, s->pcol, a);
+    NQ_LAUNCH(ctx, kern, grid, wpb * 32, smem, (const T*)m->params, (const T*)m->etab, tabc, s->prow, s->pcol, a);
     return NQ_OK;
 }
 
@@ -334,6 +343,7 @@ int dispatch_sampler_rbm(nq_sampler_t s, const RunArgs& a) {
 int run_sampler(nq_sampler_t s, const RunArgs& a) {
     nq_machine_t m = s->m;
     if (m->N > 64 * MAXW) return nq_fail(m->ctx, NQ_ERR_UNSUPPORTED, "sampler supports N <= %d", 64 * MAXW);
+    NQ_CHECK(nq_machine_ensure_tables(m));
     if (m->kind == NQ_NDM) {
         if (m->dtype == NQ_F64)
             return m->act == NQ_SOFTPLUS ? launch_sampler_ndm<double, NQ_SOFTPLUS>(s, a) : launch_sampler_ndm<double, NQ_LOGCOSH>(s, a);

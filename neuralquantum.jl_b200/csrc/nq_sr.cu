@@ -992,6 +992,7 @@ extern "C" int nq_update(nq_machine_t m, const void* dw, double eta) {
         case NQ_C64: NQ_LAUNCH(ctx, update_kernel<cxf>, g, 256, 0, (cxf*)m->params, (const cxf*)d, (float)eta, m->P); break;
         default: NQ_LAUNCH(ctx, update_kernel<cxd>, g, 256, 0, (cxd*)m->params, (const cxd*)d, eta, m->P); break;
     }
+    m->etab_valid = false;
     if (!nq_is_device_ptr(dw)) NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NQ_OK;
 }
