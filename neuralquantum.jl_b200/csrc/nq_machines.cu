@@ -347,43 +347,66 @@ __global__ void log_prob_kernel(const E* __restrict__ in, typename elem_traits<E
     if (i < n) out[i] = typename elem_traits<E>::real(2) * real_part(in[i]);
 }
 
-constexpr int NT_M = 256;
 constexpr int TB_RBM = 8;
 constexpr int TB_NDM = 4;
 
-template <typename E, int ACT, bool DOUBLED>
-int launch_rbm(nq_machine_t m, const uint64_t* prow, const uint64_t* pcol, int64_t B, void* out, void* O, int64_t ldO) {
+// threads per CTA follow the number of hidden units (one thread per unit of the current chunk): a
+// machine with 32 units runs one-warp CTAs (no barrier, 16 CTAs per SM) instead of idling 7 of 8 warps
+inline int pick_threads(int units) { return units <= 32 ? 32 : units <= 64 ? 64 : units <= 128 ? 128 : 256; }
+
+template <typename E, int ACT, bool DOUBLED, int NT>
+int launch_rbm_nt(nq_machine_t m, const uint64_t* prow, const uint64_t* pcol, int64_t B, void* out, void* O, int64_t ldO) {
     typedef typename elem_traits<E>::real T;
     nq_ctx_t ctx = m->ctx;
-    size_t smem = (size_t)2 * m->N * TB_RBM * sizeof(T) + (size_t)TB_RBM * NT_M * sizeof(E) + (NT_M / 32) * TB_RBM * sizeof(E);
+    size_t smem = (size_t)2 * m->N * TB_RBM * sizeof(T) + (size_t)TB_RBM * NT * sizeof(E) + (NT / 32) * TB_RBM * sizeof(E);
     unsigned grid = (unsigned)((B + TB_RBM - 1) / TB_RBM);
     if (O) {
-        auto kern = rbm_evalgrad_kernel<E, ACT, DOUBLED, true, TB_RBM, NT_M>;
+        auto kern = rbm_evalgrad_kernel<E, ACT, DOUBLED, true, TB_RBM, NT>;
         NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NQ_LAUNCH(ctx, kern, grid, NT_M, smem, (const E*)m->params, prow, pcol, B, m->N, m->M, (int)m->hilb, (E*)out, (E*)O, ldO);
+        NQ_LAUNCH(ctx, kern, grid, NT, smem, (const E*)m->params, prow, pcol, B, m->N, m->M, (int)m->hilb, (E*)out, (E*)O, ldO);
     } else {
-        auto kern = rbm_evalgrad_kernel<E, ACT, DOUBLED, false, TB_RBM, NT_M>;
+        auto kern = rbm_evalgrad_kernel<E, ACT, DOUBLED, false, TB_RBM, NT>;
         NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NQ_LAUNCH(ctx, kern, grid, NT_M, smem, (const E*)m->params, prow, pcol, B, m->N, m->M, (int)m->hilb, (E*)out, (E*)nullptr, ldO);
+        NQ_LAUNCH(ctx, kern, grid, NT, smem, (const E*)m->params, prow, pcol, B, m->N, m->M, (int)m->hilb, (E*)out, (E*)nullptr, ldO);
+    }
+    return NQ_OK;
+}
+
+template <typename E, int ACT, bool DOUBLED>
+int launch_rbm(nq_machine_t m, const uint64_t* prow, const uint64_t* pcol, int64_t B, void* out, void* O, int64_t ldO) {
+    switch (pick_threads(m->M)) {
+        case 32: return launch_rbm_nt<E, ACT, DOUBLED, 32>(m, prow, pcol, B, out, O, ldO);
+        case 64: return launch_rbm_nt<E, ACT, DOUBLED, 64>(m, prow, pcol, B, out, O, ldO);
+        case 128: return launch_rbm_nt<E, ACT, DOUBLED, 128>(m, prow, pcol, B, out, O, ldO);
+        default: return launch_rbm_nt<E, ACT, DOUBLED, 256>(m, prow, pcol, B, out, O, ldO);
+    }
+}
+
+template <typename T, int ACT, int NT>
+int launch_ndm_nt(nq_machine_t m, const uint64_t* prow, const uint64_t* pcol, int64_t B, void* out, void* O, int64_t ldO) {
+    nq_ctx_t ctx = m->ctx;
+    size_t smem = (size_t)2 * m->N * TB_NDM * sizeof(T) + (size_t)4 * TB_NDM * NT * sizeof(T) + (NT / 32) * TB_NDM * sizeof(cx<T>);
+    unsigned grid = (unsigned)((B + TB_NDM - 1) / TB_NDM);
+    if (O) {
+        auto kern = ndm_evalgrad_kernel<T, ACT, true, TB_NDM, NT>;
+        NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NQ_LAUNCH(ctx, kern, grid, NT, smem, (const T*)m->params, prow, pcol, B, m->N, m->M, m->A, (int)m->hilb, (cx<T>*)out, (cx<T>*)O, ldO);
+    } else {
+        auto kern = ndm_evalgrad_kernel<T, ACT, false, TB_NDM, NT>;
+        NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NQ_LAUNCH(ctx, kern, grid, NT, smem, (const T*)m->params, prow, pcol, B, m->N, m->M, m->A, (int)m->hilb, (cx<T>*)out, (cx<T>*)nullptr, ldO);
     }
     return NQ_OK;
 }
 
 template <typename T, int ACT>
 int launch_ndm(nq_machine_t m, const uint64_t* prow, const uint64_t* pcol, int64_t B, void* out, void* O, int64_t ldO) {
-    nq_ctx_t ctx = m->ctx;
-    size_t smem = (size_t)2 * m->N * TB_NDM * sizeof(T) + (size_t)4 * TB_NDM * NT_M * sizeof(T) + (NT_M / 32) * TB_NDM * sizeof(cx<T>);
-    unsigned grid = (unsigned)((B + TB_NDM - 1) / TB_NDM);
-    if (O) {
-        auto kern = ndm_evalgrad_kernel<T, ACT, true, TB_NDM, NT_M>;
-        NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NQ_LAUNCH(ctx, kern, grid, NT_M, smem, (const T*)m->params, prow, pcol, B, m->N, m->M, m->A, (int)m->hilb, (cx<T>*)out, (cx<T>*)O, ldO);
-    } else {
-        auto kern = ndm_evalgrad_kernel<T, ACT, false, TB_NDM, NT_M>;
-        NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NQ_LAUNCH(ctx, kern, grid, NT_M, smem, (const T*)m->params, prow, pcol, B, m->N, m->M, m->A, (int)m->hilb, (cx<T>*)out, (cx<T>*)nullptr, ldO);
+    switch (pick_threads(m->M > m->A ? m->M : m->A)) {
+        case 32: return launch_ndm_nt<T, ACT, 32>(m, prow, pcol, B, out, O, ldO);
+        case 64: return launch_ndm_nt<T, ACT, 64>(m, prow, pcol, B, out, O, ldO);
+        case 128: return launch_ndm_nt<T, ACT, 128>(m, prow, pcol, B, out, O, ldO);
+        default: return launch_ndm_nt<T, ACT, 256>(m, prow, pcol, B, out, O, ldO);
     }
-    return NQ_OK;
 }
 
 template <typename E>

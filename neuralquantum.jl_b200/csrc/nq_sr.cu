@@ -814,10 +814,21 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
     const int ntile = (int)((P + TS - 1) / TS);
     const int64_t Ppad = (int64_t)ntile * TS;
     const int64_t ntri = (int64_t)ntile * (ntile + 1) / 2;
-    int nsplit = (int)std::max<int64_t>(1, (4 * (int64_t)ctx->num_sms + ntri - 1) / ntri);
-    nsplit = (int)std::min<int64_t>(nsplit, std::max<int64_t>(1, Ns / (8 * KS)));
+    // split K so that the grid is close to a whole number of waves (one 256-thread CTA per SM): with
+    // 153 tiles a 4-way split runs 4.13 waves, i.e. a 5th wave that is 87% idle
     const size_t plane = (size_t)Ppad * Ppad * sizeof(double);
-    while (nsplit > 1 && plane * nsplit * (out_complex ? 2 : 1) > ((size_t)2 << 30)) nsplit--;
+    const int64_t nchunk = (Ns + KS - 1) / KS;
+    int nsplit = 1;
+    {
+        double best = 1e30;
+        for (int ns = 1; ns <= 64; ns++) {
+            if (ns > 1 && nchunk / ns < 16) break;
+            if (plane * ns * (out_complex ? 2 : 1) > ((size_t)3 << 30)) break;
+            double waves = (double)ntri * ns / ctx->num_sms;
+            double cost = std::ceil(waves) / waves + 0.002 * ns;       // tail inefficiency + partial-sum traffic
+            if (waves >= 1.0 || ns == 1) { if (cost < best) { best = cost; nsplit = ns; } }
+        }
+    }
     double* Wre = (double*)nq_scratch(ctx, SL_W0, plane * nsplit);
     double* Wim = out_complex ? (double*)nq_scratch(ctx, SL_W1, plane * nsplit) : nullptr;
     if (!Wre || (out_complex && !Wim)) return NQ_ERR_ALLOC;

@@ -12,6 +12,7 @@ from .samplers import MetropolisSampler, MetropolisSamplerCache, LocalRule
 from .algorithms import (SR, Descent, update_, local_scalar, local_grad, stat_analysis, Measurement, sr_cholesky,
                          sr_cg)
 from .iterative import BatchedSampler
+from .parallel import shard_chains, init_comm, world_from_env
 
 
 def LocalOperator(hilb):
