@@ -34,13 +34,13 @@ for algo, tol in (("sr_cholesky", 1e-9), ("sr_cg", 1e-7)):
     assert bs.Ns_total == Btot * Lc
     bs.set_samples((np.asfortranarray(R[:, off:off + B]), np.asfortranarray(Cc[:, off:off + B])))
     stat, _ = bs.sample_(sample=False)
-    dw = bs.precondition_().cpu().numpy()
     ref = OSR.iteration_liouvillian(om, ol, R.reshape(N, -1, order="F"), Cc.reshape(N, -1, order="F"), OSR.eps_f32(eps))
+    if bs.S is not None:            # compare before the solve: Cholesky factorises S in place
+        H.assert_close(bs.S.cpu().numpy().T, ref["S"], 1e-11, "S (global)")
+    dw = bs.precondition_().cpu().numpy()
     H.assert_close(bs.avg.cpu().numpy(), ref["O_avg"], 1e-11, "<O> (global)")
     H.assert_close(bs.F.cpu().numpy(), ref["F"], 1e-9, "F (global)")
     assert abs(bs.cost - ref["C"]) < 1e-11 * ref["C"]
-    if bs.S is not None:
-        H.assert_close(bs.S.cpu().numpy().T, ref["S"], 1e-11, "S (global)")
     assert np.linalg.norm(dw - ref["dw"]) <= tol * np.linalg.norm(ref["dw"]), algo
     # every rank holds the same update
     t = torch.from_numpy(dw.copy()).cuda()
