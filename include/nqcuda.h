@@ -162,6 +162,12 @@ int nq_local_scalar(nq_machine_t m, nq_operator_t op, const void* srow, const vo
  * ref: Accumulators/AccumulatorObsGrad.jl:39-127, AccumulatorLogGradPsi.jl:57-120, BatchedGradSampler.jl:87-97 */
 int nq_local_grad(nq_machine_t m, nq_operator_t op, const void* srow, const void* scol, nq_dtype sdtype,
                   int64_t B, const void* logpsi, void* out_loc, void* out_gloc, int64_t ld);
+/* fused iteration step on device-resident packed configurations: log psi [B], O [P,B] (ldO), the local
+ * estimator [B] and, for Liouvillians, its gradient [P,B] (ld; may be NULL) in one pass over the batch.
+ * ref: BatchedGradSampler.jl:83-97, BatchedValSampler.jl:122-125 */
+int nq_logpsi_grad_local_packed(nq_machine_t m, nq_operator_t op, const uint64_t* prow, const uint64_t* pcol,
+                                int64_t B, void* out_logpsi, void* O, int64_t ldO, void* out_loc, void* out_gloc,
+                                int64_t ld);
 int nq_local_scalar_packed(nq_machine_t m, nq_operator_t op, const uint64_t* prow, const uint64_t* pcol,
                            int64_t B, void* out_loc);
 int nq_local_grad_packed(nq_machine_t m, nq_operator_t op, const uint64_t* prow, const uint64_t* pcol,

@@ -44,7 +44,8 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     os.makedirs(BUILD, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
-    hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+    hdrs = (glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inc")) +
+            glob.glob(os.path.join(HERE, "..", "include", "*.h")))
     inc = ["-I", _nccl_include()]
     jobs = []
     for s in srcs:

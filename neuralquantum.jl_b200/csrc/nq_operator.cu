@@ -202,11 +202,14 @@ __device__ inline unsigned char* conn_list_carve(unsigned char* p, int cap, int 
 }
 
 #include "nq_estimators.inc"
+#include "nq_estimators_ndm3.inc"
 
 }  // namespace
 
+// out_logpsi / O may be null; when given (fused eval+grad+estimator) the machines without a fused kernel
+// run the eval+grad kernel first.
 int nq_local_device(nq_machine_t m, nq_operator_t op, const uint64_t* pr, const uint64_t* pc, int64_t B,
-                    void* out_loc, void* out_g, int64_t ld) {
+                    void* out_logpsi, void* O, int64_t ldO, void* out_loc, void* out_g, int64_t ld) {
     nq_ctx_t ctx = m->ctx;
     if (op->ctx != ctx) return nq_fail(ctx, NQ_ERR_ARG, "machine and operator belong to different contexts");
     if (op->N != m->N) return nq_fail(ctx, NQ_ERR_SHAPE, "operator acts on %d sites, machine on %d", op->N, m->N);
@@ -216,6 +219,18 @@ int nq_local_device(nq_machine_t m, nq_operator_t op, const uint64_t* pr, const 
     if (m->N > 256) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "estimator kernels index sites with 8 bits (N <= 256)");
     if (B == 0) return NQ_OK;
     NQ_CHECK(nq_machine_ensure_tables(m));
+    if (m->kind == NQ_NDM) {
+        bool used = false;
+        if (m->dtype == NQ_F64) {
+            NQ_CHECK((m->act == NQ_SOFTPLUS ? launch_local_ndm3<double, NQ_SOFTPLUS>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)
+                                             : launch_local_ndm3<double, NQ_LOGCOSH>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)));
+        } else {
+            NQ_CHECK((m->act == NQ_SOFTPLUS ? launch_local_ndm3<float, NQ_SOFTPLUS>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)
+                                             : launch_local_ndm3<float, NQ_LOGCOSH>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)));
+        }
+        if (used) return NQ_OK;
+    }
+    if (out_logpsi) NQ_CHECK(nq_machine_eval_device(m, pr, pc, B, out_logpsi, O, ldO));
     if (m->kind == NQ_NDM) {
         if (m->dtype == NQ_F64)
             return m->act == NQ_SOFTPLUS ? launch_local_ndm<double, NQ_SOFTPLUS>(m, op, pr, pc, B, out_loc, out_g, ld)
@@ -392,7 +407,7 @@ static int local_common(nq_machine_t m, nq_operator_t op, const void* srow, cons
     void* dl = st.out(SL_OUT0, out_loc, (size_t)B * cs);
     void* dg = out_g ? st.out2d(SL_OUT1, out_g, (size_t)m->P * cs, (size_t)ld * cs, (size_t)B) : nullptr;
     if (st.status != NQ_OK) return st.status;
-    NQ_CHECK(nq_local_device(m, op, pr, pc, B, dl, dg, ld));
+    NQ_CHECK(nq_local_device(m, op, pr, pc, B, nullptr, nullptr, 0, dl, dg, ld));
     return st.finish();
 }
 
@@ -413,4 +428,21 @@ extern "C" int nq_local_grad_packed(nq_machine_t m, nq_operator_t op, const uint
                                     int64_t B, void* out_loc, void* out_gloc, int64_t ld) {
     if (m && op && op->space != NQ_SUPER) return nq_fail(m->ctx, NQ_ERR_UNSUPPORTED, "gradient estimator is defined for Liouvillians only");
     return local_common(m, op, prow, pcol, NQ_F64, B, out_loc, out_gloc, ld, true);
+}
+
+// fused iteration entry: log psi, O, local estimator (and its gradient for Liouvillians) of device-resident
+// packed configurations in one pass.  ref: BatchedGradSampler.jl:83-97 / BatchedValSampler.jl:122-125
+extern "C" int nq_logpsi_grad_local_packed(nq_machine_t m, nq_operator_t op, const uint64_t* prow, const uint64_t* pcol,
+                                           int64_t B, void* out_logpsi, void* O, int64_t ldO, void* out_loc,
+                                           void* out_gloc, int64_t ld) {
+    if (!m || !op || !prow || !out_logpsi || !O || !out_loc || B < 0) return NQ_ERR_ARG;
+    nq_ctx_t ctx = m->ctx;
+    if (m->doubled() != (pcol != nullptr)) return nq_fail(ctx, NQ_ERR_ARG, "row/col configuration mismatch");
+    if (ldO < m->P || (out_gloc && ld < m->P)) return nq_fail(ctx, NQ_ERR_SHAPE, "leading dimension < P");
+    if (out_gloc && op->space != NQ_SUPER) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "gradient estimator is defined for Liouvillians only");
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!nq_is_device_ptr(prow) || !nq_is_device_ptr(O) || !nq_is_device_ptr(out_logpsi) || !nq_is_device_ptr(out_loc) ||
+        (out_gloc && !nq_is_device_ptr(out_gloc)))
+        return nq_fail(ctx, NQ_ERR_ARG, "the fused entry point works on device-resident buffers");
+    return nq_local_device(m, op, prow, pcol, B, out_logpsi, O, ldO, out_loc, out_gloc, ld);
 }

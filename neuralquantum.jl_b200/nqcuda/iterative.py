@@ -93,17 +93,12 @@ class BatchedSampler:
                                          buf.data_ptr()), ctx.h)
 
     def evaluate(self):
-        """logpsi_and_grad! + local estimator on the stored samples."""
+        """logpsi_and_grad! + local estimator on the stored samples (one fused pass)."""
         net, ctx, Ns = self.net, self.ctx, self.Ns
         pc = self.pcol.data_ptr() if self.pcol is not None else None
-        L.check(L.lib.nq_logpsi_grad_packed(net.h, self.prow.data_ptr(), pc, Ns, self.logpsi.data_ptr(),
-                                            self.O.data_ptr(), net.P), ctx.h)
-        if self.is_liouvillian:
-            L.check(L.lib.nq_local_grad_packed(net.h, self.op.h, self.prow.data_ptr(), pc, Ns, self.loc.data_ptr(),
-                                               self.gloc.data_ptr(), net.P), ctx.h)
-        else:
-            L.check(L.lib.nq_local_scalar_packed(net.h, self.op.h, self.prow.data_ptr(), pc, Ns, self.loc.data_ptr()),
-                    ctx.h)
+        gl = self.gloc.data_ptr() if self.is_liouvillian else None
+        L.check(L.lib.nq_logpsi_grad_local_packed(net.h, self.op.h, self.prow.data_ptr(), pc, Ns, self.logpsi.data_ptr(),
+                                                  self.O.data_ptr(), net.P, self.loc.data_ptr(), gl, net.P), ctx.h)
 
     def assemble(self):
         """centre O, force vector, SR setup (S, F)."""
