@@ -42,58 +42,65 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on the host cores (the one place bench.py executes oracle/)
+# CPU arm: the oracle's C restatement on the host cores (the one place bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    os.environ["OMP_NUM_THREADS"] = "1"
-    n, seed = args
-    from oracle import estimators as OE, machines as OM
-    from oracle.models import lindblad_ising_1d, random_states
-    w = WORKLOAD
-    hilb, _, _, liouv = lindblad_ising_1d(w["N"], w["g"], w["V"])
-    net = OM.random_machine("ndm", w["N"], w["alpha"], seed=1234, std=0.1)
-    sr_, sc_ = random_states(hilb, n, seed), random_states(hilb, n, seed + 1)
+_CPU_STATE = {}
+
+
+def _cpu_setup():
+    """The reference CPU path = oracle/cref.c (C restatement of the Julia algorithm, OpenMP over samples):
+    full forward pass + full gradient for every connected configuration, like AccumulatorObsGrad."""
+    if not _CPU_STATE:
+        from oracle import cref, machines as OM
+        from oracle.models import lindblad_ising_1d
+        w = WORKLOAD
+        hilb, _, _, liouv = lindblad_ising_1d(w["N"], w["g"], w["V"])
+        net = OM.random_machine("ndm", w["N"], w["alpha"], seed=1234, std=0.1)
+        _CPU_STATE.update(cref=cref, hilb=hilb, liouv=liouv, net=net, tables=cref.flatten(liouv))
+    return _CPU_STATE
+
+
+def cpu_samples_per_s(n_samples, threads):
+    """eval+grad+local estimator of n_samples configurations of the workload on `threads` host threads."""
+    from oracle.models import random_states
+    st = _cpu_setup()
+    cref, net = st["cref"], st["net"]
+    sr_, sc_ = random_states(st["hilb"], n_samples, 100), random_states(st["hilb"], n_samples, 101)
     t0 = time.perf_counter()
-    out, O = net.logpsi_grad(sr_, sc_)
-    OE.local_grad_super(net, liouv, sr_, sc_, out)
-    return time.perf_counter() - t0
+    cref.ndm_logpsi_grad(net, sr_, sc_, nthreads=threads)
+    cref.local_grad_super(net, st["liouv"], sr_, sc_, nthreads=threads, tables=st["tables"])
+    dt = time.perf_counter() - t0
+    return n_samples / dt, n_samples
 
 
-def cpu_samples_per_s(n_samples, procs):
-    """eval+grad+local estimator of the oracle port over n_samples configurations, sharded over
-    `procs` worker processes (the reference's threads+MPI = chain-sharded workers)."""
-    import multiprocessing as mp
-    per = max(1, n_samples // procs)
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(procs) as pool:
-        pool.map(_cpu_worker, [(2, 1)] * procs)                 # import + warm-up
-        t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(per, 100 + i) for i in range(procs)])
-        dt = time.perf_counter() - t0
-    return per * procs / dt, per * procs
+def _cpu_sample_size(threads, seconds):
+    v, _ = cpu_samples_per_s(64 * threads, threads)          # calibration (also warms the library)
+    n = int(v * seconds)
+    return max(64 * threads, min(WORKLOAD["chains"] * WORKLOAD["L"], (n // 1024) * 1024 or 1024))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    procs = os.cpu_count() or 1
-    n = 16 * procs
+    threads = os.cpu_count() or 1
+    n = _cpu_sample_size(threads, 4.0)
     for _ in range(args.warmup):
-        cpu_samples_per_s(procs * 2, procs)
+        cpu_samples_per_s(max(1024, n // 8), threads)
     vals = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, used = cpu_samples_per_s(n, procs)
+        v, used = cpu_samples_per_s(n, threads)
         vals.append(v)
     dt = time.perf_counter() - t0
     value = float(np.mean(vals))
-    sample = "%d configurations per step over %d worker processes (NumPy oracle port; Julia unavailable)" % (used, procs)
+    sample = ("%d configurations per step on %d OpenMP threads; C restatement of the reference algorithm "
+              "(oracle/cref.c; Julia is not installed, so the Julia code itself cannot be timed)" % (used, threads))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": procs, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -301,11 +308,12 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(2 * Ns * N * 8),
                     "d2h_bytes_per_step": int(Ns * 16), "ms_per_step": ms_e2e / args.steps}}
     if world == 1 and not args.no_cpu:
-        procs = os.cpu_count() or 1
-        v, used = cpu_samples_per_s(8 * procs, procs)
-        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": procs, "kind": "port",
-                                "sample": "%d configurations of the same workload over %d worker processes "
-                                          "(NumPy oracle port of the reference algorithm; Julia unavailable)" % (used, procs)}
+        threads = os.cpu_count() or 1
+        n = _cpu_sample_size(threads, 12.0)
+        v, used = cpu_samples_per_s(n, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+                                "sample": "%d configurations of the same workload on %d OpenMP threads; C restatement of "
+                                          "the reference algorithm (oracle/cref.c; Julia unavailable)" % (used, threads)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -157,12 +157,30 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// Which components (bit 0 = re, bit 1 = im) of each 128-row tile are not identically zero.  For the
+// real-parameter NDM the rows of the lambda-type parameters are purely real and those of the mu-type purely
+// imaginary (NDMBatched.jl:262-277), so most tile pairs need half of K and lambda x mu tiles vanish.
+template <typename T, int NC>
+__global__ void tile_activity_kernel(const T* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, unsigned* __restrict__ flags) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;      // real row index (k*NC + c)
+    if (r >= P * NC) return;
+    int64_t per = (Ns + gridDim.y - 1) / gridDim.y;
+    int64_t s0 = blockIdx.y * per, s1 = s0 + per < Ns ? s0 + per : Ns;
+    bool nz = false;
+    for (int64_t s = s0; s < s1; s++) nz |= Xr[r + ldr * s] != T(0);
+    if (nz) atomicOr(&flags[(r / NC) / TS], 1u << (r % NC));
+}
+
+constexpr int LDP = TS + 8;                 // one sample of one component plane, padded (bank-conflict free)
+constexpr int PLANE = KS * LDP + 8;         // component plane
+
 template <typename T, int NC>
 __global__ void __launch_bounds__(256, 1)
 syrk_dmma_kernel(const T* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, int ntile, int nsplit, int mode,
+                 const unsigned* __restrict__ tflags,
                  double* __restrict__ Wk /* [nsplit][Ppad*Ppad] col-major, Ppad = ntile*TS */) {
-    constexpr int LD = TS * NC + (NC == 2 ? 8 : 4);     // padded row (one sample) of a tile, in doubles
     constexpr int PER = TS * NC * KS / 256;             // reals per thread per tile per chunk
+    constexpr int TILE = NC * PLANE;                    // doubles per staged tile
     extern __shared__ __align__(16) double smem[];
     // decode lower-triangular tile index
     int t = blockIdx.x;
@@ -176,11 +194,25 @@ syrk_dmma_kernel(const T* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, i
     const int64_t cper = (nchunk_tot + nsplit - 1) / nsplit;
     const int64_t c_begin = split * cper, c_end = std::min<int64_t>(nchunk_tot, c_begin + cper);
 
-    double* As[2] = {smem, smem + 2 * KS * LD};
-    double* Bs[2] = {smem + KS * LD, smem + 3 * KS * LD};
+    double* As[2] = {smem, smem + 2 * TILE};
+    double* Bs[2] = {smem + TILE, smem + 3 * TILE};
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tq = lane & 3;
     const int wm = warp & 1, wn = warp >> 1;
+
+    // component pairs that contribute: mode 0 pairs (c, c); mode 1 pairs (c of A, 1-c of B)
+    const unsigned fa = NC == 2 ? tflags[ti] : 1u, fb = NC == 2 ? tflags[tj] : 1u;
+    unsigned act = 0;                       // bit c: component c of A is used
+    for (int c = 0; c < NC; c++) {
+        unsigned bc = mode == 0 ? c : 1 - c;
+        if (((fa >> c) & 1u) && ((fb >> bc) & 1u)) act |= 1u << c;
+    }
+    unsigned needA = act, needB = 0;
+    for (int c = 0; c < NC; c++) if ((act >> c) & 1u) needB |= 1u << (mode == 0 ? c : 1 - c);
+    if (diag) needA |= needB;
+    // a thread always loads the same component: r = (tid + 256 i) % (TS*NC) has the parity of tid
+    const int myc = NC == 2 ? (tid & 1) : 0;
+    const bool ldA = (needA >> myc) & 1u, ldB = !diag && ((needB >> myc) & 1u);
 
     double acc[8][4][2];
 #pragma unroll
@@ -197,9 +229,9 @@ syrk_dmma_kernel(const T* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, i
             int e = tid + 256 * i;               // e = s * (TS*NC) + r
             int s = e / (TS * NC), r = e - s * (TS * NC);
             int64_t smp = chunk * KS + s;
-            bool okA = smp < Ns && rowA + r < PR, okB = smp < Ns && rowB + r < PR;
+            bool okA = ldA && smp < Ns && rowA + r < PR, okB = ldB && smp < Ns && rowB + r < PR;
             ra[i] = okA ? Xr[rowA + r + ldr * smp] : T(0);
-            if (!diag) rbv[i] = okB ? Xr[rowB + r + ldr * smp] : T(0);
+            rbv[i] = okB ? Xr[rowB + r + ldr * smp] : T(0);
         }
     };
     auto sstore = [&](int buf) {
@@ -207,47 +239,46 @@ syrk_dmma_kernel(const T* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, i
         for (int i = 0; i < PER; i++) {
             int e = tid + 256 * i;
             int s = e / (TS * NC), r = e - s * (TS * NC);
-            As[buf][s * LD + r] = (double)ra[i];
-            if (!diag) Bs[buf][s * LD + r] = (double)rbv[i];
+            int m = r / NC;
+            if (ldA) As[buf][myc * PLANE + s * LDP + m] = (double)ra[i];
+            if (ldB) Bs[buf][myc * PLANE + s * LDP + m] = (double)rbv[i];
         }
     };
 
-    if (c_begin < c_end) {
+    if (act && c_begin < c_end) {
         gload(c_begin);
         sstore(0);
     }
     __syncthreads();
-    for (int64_t c = c_begin; c < c_end; c++) {
-        const int buf = (int)((c - c_begin) & 1);
-        if (c + 1 < c_end) gload(c + 1);
-        const double* A = As[buf];
-        const double* Bm = diag ? As[buf] : Bs[buf];
+    if (act) {
+        for (int64_t c = c_begin; c < c_end; c++) {
+            const int buf = (int)((c - c_begin) & 1);
+            if (c + 1 < c_end) gload(c + 1);
+            const double* A = As[buf];
+            const double* Bm = diag ? As[buf] : Bs[buf];
 #pragma unroll
-        for (int k4 = 0; k4 < KS * NC / 4; k4++) {
-            // logical k index kk = 4*k4 + tq -> (sample, component)
-            const int kk = 4 * k4 + tq;
-            const int s = NC == 2 ? (kk >> 1) : kk;
-            const int cc = NC == 2 ? (kk & 1) : 0;
-            double a[8], b[4];
+            for (int comp = 0; comp < NC; comp++) {
+                if (!((act >> comp) & 1u)) continue;
+                const int bcomp = mode == 0 ? comp : 1 - comp;
+                const double* Ap = A + comp * PLANE + wm * 64 + g;
+                const double* Bp = Bm + bcomp * PLANE + wn * 32 + g;
 #pragma unroll
-            for (int i = 0; i < 8; i++) a[i] = A[s * LD + (wm * 64 + i * 8 + g) * NC + cc];
-            if (mode == 0) {
+                for (int k4 = 0; k4 < KS / 4; k4++) {
+                    const int sidx = (4 * k4 + tq) * LDP;
+                    double a[8], b[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) b[j] = Bm[s * LD + (wn * 32 + j * 8 + g) * NC + cc];
-            } else {
+                    for (int i = 0; i < 8; i++) a[i] = Ap[sidx + i * 8];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    double v = Bm[s * LD + (wn * 32 + j * 8 + g) * NC + (1 - cc)];
-                    b[j] = cc ? -v : v;
+                    for (int j = 0; j < 4; j++) { double v = Bp[sidx + j * 8]; b[j] = (mode == 1 && comp == 1) ? -v : v; }
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            if (c + 1 < c_end) sstore(buf ^ 1);
+            __syncthreads();
         }
-        if (c + 1 < c_end) sstore(buf ^ 1);
-        __syncthreads();
     }
     const int64_t Ppad = (int64_t)ntile * TS;
     double* W = Wk + (size_t)split * Ppad * Ppad;
@@ -284,12 +315,18 @@ __global__ void syrk_finalize_kernel(const double* __restrict__ Wre, const doubl
 
 template <typename T, int NC>
 int launch_syrk(nq_ctx_t ctx, const void* X, int64_t ldr, int64_t P, int64_t Ns, int ntile, int nsplit, int mode, double* W) {
-    constexpr int LD = TS * NC + (NC == 2 ? 8 : 4);
-    size_t smem = (size_t)4 * KS * LD * sizeof(double);
+    size_t smem = (size_t)4 * NC * PLANE * sizeof(double);
+    unsigned* flags = (unsigned*)nq_scratch(ctx, SL_W3, (size_t)ntile * sizeof(unsigned) + 16);
+    if (!flags) return NQ_ERR_ALLOC;
+    if (NC == 2 && mode == 0) {       // mode 1 (same launch sequence) reuses the flags
+        NQ_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)ntile * sizeof(unsigned), ctx->stream));
+        dim3 g((unsigned)((P * NC + 255) / 256), (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, Ns / 64)));
+        NQ_LAUNCH(ctx, (tile_activity_kernel<T, NC>), g, 256, 0, (const T*)X, ldr, P, Ns, flags);
+    }
     auto kern = syrk_dmma_kernel<T, NC>;
     NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(ntile * (ntile + 1) / 2), (unsigned)nsplit);
-    NQ_LAUNCH(ctx, kern, grid, 256, smem, (const T*)X, ldr, P, Ns, ntile, nsplit, mode, W);
+    NQ_LAUNCH(ctx, kern, grid, 256, smem, (const T*)X, ldr, P, Ns, ntile, nsplit, mode, (const unsigned*)flags, W);
     return NQ_OK;
 }
 
