@@ -74,7 +74,8 @@ def cpu_samples_per_s(n_samples, threads):
 
 
 def _cpu_sample_size(threads, seconds):
-    v, _ = cpu_samples_per_s(64 * threads, threads)          # calibration (also warms the library)
+    cpu_samples_per_s(16 * threads, threads)                 # load the library, start the OpenMP team
+    v, _ = cpu_samples_per_s(128 * threads, threads)         # calibration
     n = int(v * seconds)
     return max(64 * threads, min(WORKLOAD["chains"] * WORKLOAD["L"], (n // 1024) * 1024 or 1024))
 

@@ -446,3 +446,12 @@ extern "C" int nq_logpsi_grad_local_packed(nq_machine_t m, nq_operator_t op, con
         return nq_fail(ctx, NQ_ERR_ARG, "the fused entry point works on device-resident buffers");
     return nq_local_device(m, op, prow, pcol, B, out_logpsi, O, ldO, out_loc, out_gloc, ld);
 }
+
+#ifdef NQ_PROFILE_PHASES
+extern "C" int nq_debug_phase_cycles(unsigned long long out[8], int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, nq_phase_cycles, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(nq_phase_cycles, z, sizeof z); }
+    return 0;
+}
+#endif

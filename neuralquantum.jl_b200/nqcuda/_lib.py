@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(HERE), "libnqcuda.so")
+LIB_PATH = os.environ.get("NQCUDA_LIB", os.path.join(os.path.dirname(HERE), "libnqcuda.so"))
 
 # enums (mirror include/nqcuda.h)
 NQ_OK = 0
