@@ -56,3 +56,6 @@ int nq_machine_eval_device(nq_machine_t m, const uint64_t* prow, const uint64_t*
 struct NqStage;
 int nq_stage_pack(nq_machine_t m, NqStage& st, const void* srow, const void* scol, nq_dtype sdtype, int64_t B,
                   const uint64_t** prow, const uint64_t** pcol);
+// nq_syrk_tf32.cu: FP32-mode S assembly on tcgen05 (3xTF32); S written as float / interleaved complex float
+int nq_syrk_tf32_device(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total, bool o_complex,
+                        bool out_complex, void* dS);

@@ -13,6 +13,8 @@
 //      SR_notfull.jl:47-148, Optimisers/rules.jl:11-17, utils/stats.jl:26-50.
 #include "nq_internal.cuh"
 #include <algorithm>
+#include <cstring>
+#include <cstdlib>
 
 int nq_allreduce_device(nq_ctx_t ctx, void* buf, int64_t n, nq_dtype dtype, bool mean);
 
@@ -866,10 +868,16 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
             if (waves >= 1.0 || ns == 1) { if (cost < best) { best = cost; nsplit = ns; } }
         }
     }
+    const int64_t ldr = ldO * (ocx ? 2 : 1);
+    // FP32 mode: tcgen05 3xTF32 path (nq_syrk_tf32.cu) when the rows allow 16-byte loads
+    static const bool fp32_dmma = [] { const char* e = getenv("NQ_SR_FP32_PATH"); return e && !strcmp(e, "dmma"); }();
+    const bool use_tf32 = !nq_dtype_is_double(dtype) && !fp32_dmma && (ldr % 4 == 0) && ((uintptr_t)Oc % 16 == 0);
+    if (use_tf32) {
+        NQ_CHECK(nq_syrk_tf32_device(ctx, Oc, ldO, P, Ns, Ns_total, ocx, out_complex, dS));
+    } else {
     double* Wre = (double*)nq_scratch(ctx, SL_W0, plane * nsplit);
     double* Wim = out_complex ? (double*)nq_scratch(ctx, SL_W1, plane * nsplit) : nullptr;
     if (!Wre || (out_complex && !Wim)) return NQ_ERR_ALLOC;
-    const int64_t ldr = ldO * (ocx ? 2 : 1);
     if (ocx) {
         if (nq_dtype_is_double(dtype)) {
             NQ_CHECK((launch_syrk<double, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
@@ -888,6 +896,7 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
         NQ_LAUNCH(ctx, syrk_finalize_kernel<double>, grid, 128, 0, (const double*)Wre, (const double*)Wim, nsplit, Ppad, P, scale, (int)out_complex, (double*)dS);
     else
         NQ_LAUNCH(ctx, syrk_finalize_kernel<float>, grid, 128, 0, (const double*)Wre, (const double*)Wim, nsplit, Ppad, P, scale, (int)out_complex, (float*)dS);
+    }
     // F = gradC (complex nets) or Re(gradC)
     cxd* tmp = (cxd*)nq_scratch(ctx, SL_W2, (size_t)P * sizeof(cxd));
     if (!tmp) return NQ_ERR_ALLOC;

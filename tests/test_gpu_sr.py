@@ -63,6 +63,37 @@ def test_center_force_setup(nq, ctx, dtype, P, Ns, real_params):
         assert np.allclose(S, S.conj().T, atol=0)          # Hermitian by construction (mirrored tiles)
 
 
+@pytest.mark.parametrize("dtype,P,Ns,real_params,structured", [
+    (np.complex64, 256, 5000, False, False), (np.complex64, 300, 4100, True, False),
+    (np.float32, 260, 3000, True, False), (np.complex64, 516, 3001, True, True),
+    (np.float32, 132, 70000, True, False), (np.complex64, 64, 40, False, False)])
+def test_sr_setup_fp32_tensor_path(nq, ctx, dtype, P, Ns, real_params, structured):
+    """FP32-mode S assembly runs on tcgen05 (3xTF32, nq_syrk_tf32.cu); tolerance 1e-5 vs the FP64 oracle."""
+    L = nq._lib
+    rng = np.random.default_rng(11)
+    dtype = np.dtype(dtype)
+    O = _rand(rng, (P, Ns), dtype)
+    if structured:                       # real-parameter NDM: lambda rows real, mu rows imaginary
+        O[: P // 3] = O[: P // 3].real
+        O[P // 3:] = 1j * O[P // 3:].imag
+    O -= O.mean(axis=1, keepdims=True)
+    O64 = O.astype(np.complex128 if dtype.kind == "c" else np.float64)
+    dO = _dev(O)
+    g = _rand(rng, P, np.complex64)
+    sdt = np.dtype(dtype if (dtype.kind == "c" and not real_params) else np.float32)
+    S = np.zeros((P, P), sdt, order="F")
+    F = np.zeros(P, sdt)
+    L.check(L.lib.nq_sr_setup(ctx.h, dO.data_ptr(), P, P, Ns, Ns, L.nq_dtype(dtype), L.ptr(g), int(real_params),
+                              L.ptr(S), L.ptr(F)), ctx.h)
+    rS, rF = OSR.sr_setup(O64, g.astype(np.complex128), real_params)
+    # entries of S are sums of Ns products of O(1) numbers / Ns: tolerance relative to the diagonal scale
+    scale = float(np.abs(np.diag(rS)).max())
+    assert np.max(np.abs(S - rS)) <= 1e-5 * scale, np.max(np.abs(S - rS)) / scale
+    H.assert_close(F, rF, 1e-5, "F")
+    if sdt.kind == "c":
+        assert np.allclose(S, S.conj().T, atol=0)
+
+
 def test_force_liouvillian(nq, ctx):
     L = nq._lib
     rng = np.random.default_rng(6)
