@@ -45,6 +45,9 @@ struct nq_operator_s {
     uint32_t* entry_flip;   // [n_entries]
     int32_t* term_left;     // [n_terms]
     int32_t* term_right;    // [n_terms]
+    // flat records (N <= 64): [n_recs][8] = rmask, rval, cmask, cval, rflip, cflip, mel_re, mel_im (doubles as bits)
+    uint64_t* recs;
+    int n_recs;
 };
 
 // device-pointer internals shared between translation units

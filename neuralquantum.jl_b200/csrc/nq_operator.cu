@@ -27,6 +27,8 @@ struct OpDev {
     const uint32_t* entry_flip;
     const int32_t* term_left;
     const int32_t* term_right;
+    const uint64_t* recs;   // flat (condition, flips, mel) records, see nq_operator_create
+    int n_recs;
 };
 
 OpDev op_dev(nq_operator_t op) {
@@ -35,6 +37,7 @@ OpDev op_dev(nq_operator_t op) {
     d.part_nsites = op->part_nsites; d.part_site_ptr = op->part_site_ptr; d.part_sites = op->part_sites;
     d.part_row0 = op->part_row0; d.row_ptr = op->row_ptr; d.entry_mel = op->entry_mel;
     d.entry_flip = op->entry_flip; d.term_left = op->term_left; d.term_right = op->term_right;
+    d.recs = op->recs; d.n_recs = op->n_recs;
     return d;
 }
 
@@ -263,6 +266,7 @@ extern "C" int nq_operator_destroy(nq_operator_t op) {
     cudaStreamSynchronize(op->ctx->stream);
     cudaFree(op->part_nsites); cudaFree(op->part_site_ptr); cudaFree(op->part_sites); cudaFree(op->part_row0);
     cudaFree(op->row_ptr); cudaFree(op->entry_mel); cudaFree(op->entry_flip); cudaFree(op->term_left); cudaFree(op->term_right);
+    cudaFree(op->recs);
     delete op;
     return NQ_OK;
 }
@@ -346,6 +350,52 @@ extern "C" int nq_operator_create(nq_ctx_t ctx, nq_space space, int N, int n_par
         (s = upload(ctx, &op->entry_flip, entry_flip, n_entries)) == NQ_OK &&
         (s = upload(ctx, &op->term_left, term_left, n_terms)) == NQ_OK &&
         (s = upload(ctx, &op->term_right, tr.data(), n_terms)) == NQ_OK) {
+        // Flat records for N <= 64: one per (term, local row[, local row'], entry[, entry']) with non-zero matrix
+        // element, in reference order: "if (sigma & rmask) == rval and (sigma' & cmask) == cval then this
+        // connection exists, flips rflip / cflip and weighs mel".  The estimator kernels test all records
+        // in parallel instead of chasing term -> part -> row -> entry pointers per configuration.
+        std::vector<uint64_t> recs;
+        bool flat = N <= 64;
+        auto bits_of = [](double v) { uint64_t u; memcpy(&u, &v, 8); return u; };
+        for (int t = 0; t < n_terms && flat; t++) {
+            const int L = term_left[t], R = tr[t];
+            const int kl = L >= 0 ? part_nsites[L] : 0, kr = R >= 0 ? part_nsites[R] : 0;
+            const int32_t* sl = L >= 0 ? part_sites + site_ptr[L] : nullptr;
+            const int32_t* sr = R >= 0 ? part_sites + site_ptr[R] : nullptr;
+            auto site_mask = [](const int32_t* ps, int k, uint32_t local) {
+                uint64_t m = 0;
+                for (int i = 0; i < k; i++) if ((local >> i) & 1u) m |= (uint64_t)1 << ps[i];
+                return m;
+            };
+            for (int64_t rl = 0; rl < ((int64_t)1 << kl) && flat; rl++)
+                for (int64_t rr = 0; rr < ((int64_t)1 << kr) && flat; rr++) {
+                    const int64_t l0 = L >= 0 ? row_ptr[row0[L] + rl] : 0, l1 = L >= 0 ? row_ptr[row0[L] + rl + 1] : 1;
+                    const int64_t r0 = R >= 0 ? row_ptr[row0[R] + rr] : 0, r1 = R >= 0 ? row_ptr[row0[R] + rr + 1] : 1;
+                    for (int64_t el = l0; el < l1; el++)
+                        for (int64_t er = r0; er < r1; er++) {
+                            double mr, mi;
+                            if (L >= 0 && R >= 0) {
+                                const double ar = entry_mel[2 * el], ai = entry_mel[2 * el + 1], br = entry_mel[2 * er], bi = entry_mel[2 * er + 1];
+                                volatile double p0 = ar * br, p1 = ai * bi, p2 = ar * bi, p3 = ai * br;   // no contraction
+                                mr = p0 - p1; mi = p2 + p3;
+                            } else {
+                                const int64_t e = L >= 0 ? el : er;
+                                mr = entry_mel[2 * e]; mi = entry_mel[2 * e + 1];
+                            }
+                            if (mr == 0.0 && mi == 0.0) continue;
+                            const uint64_t rec[8] = {site_mask(sl, kl, (1u << kl) - 1u), site_mask(sl, kl, (uint32_t)rl),
+                                                     site_mask(sr, kr, (1u << kr) - 1u), site_mask(sr, kr, (uint32_t)rr),
+                                                     L >= 0 ? site_mask(sl, kl, entry_flip[el]) : 0, R >= 0 ? site_mask(sr, kr, entry_flip[er]) : 0,
+                                                     bits_of(mr), bits_of(mi)};
+                            recs.insert(recs.end(), rec, rec + 8);
+                            if (recs.size() > (size_t)8 << 16) flat = false;
+                        }
+                }
+        }
+        if (flat && !recs.empty()) {
+            if ((s = upload(ctx, &op->recs, recs.data(), (int64_t)recs.size())) != NQ_OK) { nq_operator_destroy(op); return s; }
+            op->n_recs = (int)(recs.size() / 8);
+        }
         *out = op;
         return NQ_OK;
     }

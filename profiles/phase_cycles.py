@@ -30,9 +30,10 @@ lib = nq._lib.lib
 lib.nq_debug_phase_cycles(out, 1)
 bs.evaluate()
 lib.nq_debug_phase_cycles(out, 0)
-names = ["decode+conn list", "base+zero", "phase AB", "phase C", "totals+A", "output"]
+names = ["decode+conn list / operator pass", "base(+zero)", "phase AB / site phase", "phase C", "totals+A", "output"]
 tot = sum(out[:6])
 for n, v in zip(names, out):
-    print("%-18s %6.1f%%  %8.0f cycles/sample" % (n, 100.0 * v / tot, v / (w["chains"] * w["L"])))
-if out[7]:
+    print("%-38s %6.1f%%  %8.0f cycles/sample" % (n, 100.0 * v / tot, v / (w["chains"] * w["L"])))
+print("raw slots 3/6/7 per sample:", [round(out[i] / (w["chains"] * w["L"])) for i in (3, 6, 7)])
+if False:
     print("phase C fast-path bodies of warp 0: %.0f cycles each, %.2f per sample" % (out[6] / out[7], out[7] / (w["chains"] * w["L"])))
