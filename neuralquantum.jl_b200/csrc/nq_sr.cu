@@ -295,6 +295,128 @@ syrk_dmma_kernel(const T* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, i
         }
 }
 
+// ---- FP64 operands: cp.async pipeline (no register staging), 4 stages of 8 samples, one barrier per chunk.
+// Plane row pitch LDQ = 132 doubles: the fragment loads (lanes g -> consecutive rows, tq -> consecutive
+// samples) hit 4 x 8 distinct banks per half-warp.
+constexpr int LDQ = TS + 4;
+constexpr int PLQ = KS * LDQ;               // doubles per component plane
+constexpr int NSTAGE = 4;
+
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int sz = valid ? 8 : 0;           // src-size 0: zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int NC>
+__global__ void __launch_bounds__(256, 1)
+syrk_dmma2_kernel(const double* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, int ntile, int nsplit, int mode,
+                  const unsigned* __restrict__ tflags, double* __restrict__ Wk) {
+    constexpr int PER = TS * NC * KS / 256;             // elements per thread per tile per chunk
+    constexpr int TILE = NC * PLQ;                      // doubles per staged tile
+    constexpr int STG = 2 * TILE;                       // A tile | B tile
+    extern __shared__ __align__(16) double smem[];
+    int t = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+    while (ti * (ti + 1) / 2 > t) ti--;
+    const int tj = t - ti * (ti + 1) / 2;
+    const bool diag = ti == tj;
+    const int split = blockIdx.y;
+    const int64_t nchunk_tot = (Ns + KS - 1) / KS;
+    const int64_t cper = (nchunk_tot + nsplit - 1) / nsplit;
+    const int64_t c_begin = split * cper, c_end = std::min<int64_t>(nchunk_tot, c_begin + cper);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tq = lane & 3;
+    const int wm = warp & 1, wn = warp >> 1;
+
+    const unsigned fa = NC == 2 ? tflags[ti] : 1u, fb = NC == 2 ? tflags[tj] : 1u;
+    unsigned act = 0;
+    for (int c = 0; c < NC; c++) {
+        unsigned bc = mode == 0 ? c : 1 - c;
+        if (((fa >> c) & 1u) && ((fb >> bc) & 1u)) act |= 1u << c;
+    }
+    unsigned needA = act, needB = 0;
+    for (int c = 0; c < NC; c++) if ((act >> c) & 1u) needB |= 1u << (mode == 0 ? c : 1 - c);
+    if (diag) needA |= needB;
+    const int myc = NC == 2 ? (tid & 1) : 0;            // a thread always copies the same component
+    const bool ldA = (needA >> myc) & 1u, ldB = !diag && ((needB >> myc) & 1u);
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    const int64_t rowA = (int64_t)ti * TS * NC, rowB = (int64_t)tj * TS * NC, PR = P * NC;
+    // per-thread copy coordinates: e = tid + 256 i = s * (TS*NC) + r
+    auto issue = [&](int64_t chunk, int stage) {
+        double* As = smem + stage * STG;
+        double* Bs = As + TILE;
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const int e = tid + 256 * i;
+            const int s = e / (TS * NC), r = e - s * (TS * NC);
+            const int64_t smp = chunk * KS + s;
+            const int dst = myc * PLQ + s * LDQ + r / NC;
+            if (ldA) { const bool ok = smp < Ns && rowA + r < PR; cp_async8(As + dst, Xr + (ok ? rowA + r + ldr * smp : 0), ok); }
+            if (ldB) { const bool ok = smp < Ns && rowB + r < PR; cp_async8(Bs + dst, Xr + (ok ? rowB + r + ldr * smp : 0), ok); }
+        }
+    };
+
+    if (act) {
+        const int64_t nch = c_end - c_begin;
+#pragma unroll
+        for (int p = 0; p < NSTAGE - 1; p++) {
+            if (p < nch) issue(c_begin + p, p);
+            cp_async_commit();
+        }
+        for (int64_t it = 0; it < nch; it++) {
+            cp_async_wait<NSTAGE - 2>();                // chunk `it` has landed (this thread's copies)
+            __syncthreads();                            // ... everyone's; and stage (it-1) % NSTAGE is free again
+            if (it + NSTAGE - 1 < nch) issue(c_begin + it + NSTAGE - 1, (int)((it + NSTAGE - 1) % NSTAGE));
+            cp_async_commit();
+            const double* A = smem + (int)(it % NSTAGE) * STG;
+            const double* Bm = diag ? A : A + TILE;
+#pragma unroll
+            for (int comp = 0; comp < NC; comp++) {
+                if (!((act >> comp) & 1u)) continue;
+                const int bcomp = mode == 0 ? comp : 1 - comp;
+                const double* Ap = A + comp * PLQ + wm * 64 + g;
+                const double* Bp = Bm + bcomp * PLQ + wn * 32 + g;
+                const bool neg = mode == 1 && comp == 1;
+#pragma unroll
+                for (int k4 = 0; k4 < KS / 4; k4++) {
+                    const int sidx = (4 * k4 + tq) * LDQ;
+                    double a[8], b[4];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) a[i] = Ap[sidx + i * 8];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { double v = Bp[sidx + j * 8]; b[j] = neg ? -v : v; }
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                }
+            }
+        }
+        cp_async_wait<0>();
+    }
+    const int64_t Ppad = (int64_t)ntile * TS;
+    double* W = Wk + (size_t)split * Ppad * Ppad;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int64_t row = (int64_t)ti * TS + wm * 64 + i * 8 + g;
+            int64_t col = (int64_t)tj * TS + wn * 32 + j * 8 + 2 * tq;
+            W[row + Ppad * col] = acc[i][j][0];
+            W[row + Ppad * (col + 1)] = acc[i][j][1];
+        }
+}
+
 // S[k,l] from the lower tile triangle: sum the splits in order, scale, mirror (Hermitian)
 // out_complex: S complex (re from Wre, im from Wim); else real.
 template <typename TS_>
@@ -325,9 +447,17 @@ int launch_syrk(nq_ctx_t ctx, const void* X, int64_t ldr, int64_t P, int64_t Ns,
         dim3 g((unsigned)((P * NC + 255) / 256), (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, Ns / 64)));
         NQ_LAUNCH(ctx, (tile_activity_kernel<T, NC>), g, 256, 0, (const T*)X, ldr, P, Ns, flags);
     }
+    dim3 grid((unsigned)(ntile * (ntile + 1) / 2), (unsigned)nsplit);
+    static const bool old_path = [] { const char* e = getenv("NQ_SYRK_PATH"); return e && !strcmp(e, "staged"); }();
+    if (sizeof(T) == 8 && !old_path) {
+        auto kern2 = syrk_dmma2_kernel<NC>;
+        size_t smem2 = (size_t)NSTAGE * 2 * NC * PLQ * sizeof(double);
+        NQ_CUDA(ctx, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        NQ_LAUNCH(ctx, kern2, grid, 256, smem2, (const double*)X, ldr, P, Ns, ntile, nsplit, mode, (const unsigned*)flags, W);
+        return NQ_OK;
+    }
     auto kern = syrk_dmma_kernel<T, NC>;
     NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)(ntile * (ntile + 1) / 2), (unsigned)nsplit);
     NQ_LAUNCH(ctx, kern, grid, 256, smem, (const T*)X, ldr, P, Ns, ntile, nsplit, mode, (const unsigned*)flags, W);
     return NQ_OK;
 }
