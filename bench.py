@@ -109,6 +109,9 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+FP64_TENSOR_PEAK = 37.2   # TFLOP/s, mma.sync m8n8k4 f64 at 8 warps/SM on this pool's B200 (profiles/fp64_peaks.json)
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -121,6 +124,10 @@ class ClockSampler:
                                        "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+        # nvidia-smi needs a moment to start: wait for its first line so that short timed regions are covered
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < 3.0 and os.path.getsize(self.f.name) == 0:
+            time.sleep(0.02)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -241,8 +248,6 @@ def run_gpu(args):
     barrier()
     t_eval = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     t_loc = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
-    clk = clocks.stop()
-
     # ---- full SR iteration ----
     opt = nq.Descent(w["eta"])
 
@@ -267,6 +272,28 @@ def run_gpu(args):
         phase("solve", bs.precondition_)
         phase("update", lambda: bs.update_(opt))
     phases = {k: v / 2 for k, v in phases.items()}
+    # ---- S assembly alone (nq_sr_setup on the centred rows of the last iteration): tensor-pipe roofline ----
+    oc = L_.nq_dtype(net.out_dtype)
+
+    def k_setup():
+        L_.check(L_.lib.nq_sr_setup(ctx.h, bs.O.data_ptr(), P, P, Ns, bs.Ns_total, oc, bs.gradC.data_ptr(),
+                                    int(bs.real_params), bs.S.data_ptr(), bs.F.data_ptr()), ctx.h)
+    k_setup()
+    a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a_.record()
+    for _ in range(3):
+        k_setup()
+    b_.record()
+    torch.cuda.synchronize()
+    t_setup = a_.elapsed_time(b_) / 3
+    # DMMA work issued: (tile pair, component) units whose planes are not identically zero, 128 x 128 x Ns MACs each
+    Ov = torch.view_as_real(bs.O) if bs.O.is_complex() else bs.O.unsqueeze(-1)
+    nzp = (Ov != 0).any(dim=0)                                   # [P, NC]
+    ntile = (P + 127) // 128
+    fl = [[bool(nzp[t * 128:(t + 1) * 128, c].any()) for c in range(nzp.shape[1])] for t in range(ntile)]
+    units = sum(sum(1 for c in range(len(fl[0])) if fl[i][c] and fl[j][c]) for i in range(ntile) for j in range(i + 1))
+    flops_setup = units * 128.0 * 128.0 * Ns * 2.0
     # restore the synthetic configurations (the SR iterations above sampled new ones)
     bs.set_samples(sig)
 
@@ -279,6 +306,7 @@ def run_gpu(args):
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = Ns_global * args.steps / (ms_e2e * 1e-3)
+    clk = clocks.stop()      # sampled over every timed region above (headline, per-kernel, SR iteration, e2e)
 
     if rank != 0:
         if world > 1:
@@ -289,14 +317,19 @@ def run_gpu(args):
     bytes_eval = Ns * (P * es + es + 2 * 8)               # O row + log rho + two packed words per configuration
     bytes_fused = Ns * (2 * P * es + 2 * es + 2 * 8)      # O row + grad L_loc row + log rho + L_loc + packed words
     ach = bytes_fused / (t_loc * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "local_ndm3_kernel<double,softplus,grad,with_O> (fused eval+grad+estimator)",
+    roof = {"bound": "hbm", "kernel": "local_ndm3s_kernel<double,softplus,grad,with_O> (fused eval+grad+estimator)",
             "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
             "peak_source": pk_kind, "ms_per_launch": t_loc, "algorithmic_bytes_per_launch": bytes_fused,
             "note": "the kernel is FP64-issue bound, not HBM bound: see DESIGN.md section 4",
             "all": {"ndm_evalgrad_kernel (stand-alone nq_logpsi_grad)": {
                         "ms": t_eval, "GB/s": bytes_eval / (t_eval * 1e-3) / 1e9,
                         "frac": bytes_eval / (t_eval * 1e-3) / 1e9 / pk["hbm_gbs"]},
-                    "local_ndm3_kernel (fused)": {"ms": t_loc, "GB/s": ach, "frac": ach / pk["hbm_gbs"]}}}
+                    "local_ndm3s_kernel (fused)": {"ms": t_loc, "GB/s": ach, "frac": ach / pk["hbm_gbs"]},
+                    "syrk_dmma2_kernel (S assembly, nq_sr_setup)": {
+                        "bound": "tensor", "ms": t_setup, "achieved": flops_setup / (t_setup * 1e-3) / 1e12, "unit": "TFLOP/s",
+                        "peak": FP64_TENSOR_PEAK, "frac": flops_setup / (t_setup * 1e-3) / 1e12 / FP64_TENSOR_PEAK,
+                        "peak_source": "FP64 DMMA issue rate measured with profiles/probe/dmma_probe.cu (cuBLAS DGEMM: 35.5)",
+                        "flops": "non-zero (tile pair, component) units x 128 x 128 x Ns x 2"}}}
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -310,13 +310,14 @@ __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src, b
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-template <int NC>
+template <int NC, int MODE>
 __global__ void __launch_bounds__(256, 1)
-syrk_dmma2_kernel(const double* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, int ntile, int nsplit, int mode,
+syrk_dmma2_kernel(const double* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, int ntile, int nsplit,
                   const unsigned* __restrict__ tflags, double* __restrict__ Wk) {
     constexpr int PER = TS * NC * KS / 256;             // elements per thread per tile per chunk
     constexpr int TILE = NC * PLQ;                      // doubles per staged tile
     constexpr int STG = 2 * TILE;                       // A tile | B tile
+    constexpr int SPI = 256 / (TS * NC);                // samples covered by one pass of the 256 threads (1 or 2)
     extern __shared__ __align__(16) double smem[];
     int t = blockIdx.x;
     int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
@@ -335,14 +336,12 @@ syrk_dmma2_kernel(const double* __restrict__ Xr, int64_t ldr, int64_t P, int64_t
     const unsigned fa = NC == 2 ? tflags[ti] : 1u, fb = NC == 2 ? tflags[tj] : 1u;
     unsigned act = 0;
     for (int c = 0; c < NC; c++) {
-        unsigned bc = mode == 0 ? c : 1 - c;
+        unsigned bc = MODE == 0 ? c : 1 - c;
         if (((fa >> c) & 1u) && ((fb >> bc) & 1u)) act |= 1u << c;
     }
     unsigned needA = act, needB = 0;
-    for (int c = 0; c < NC; c++) if ((act >> c) & 1u) needB |= 1u << (mode == 0 ? c : 1 - c);
+    for (int c = 0; c < NC; c++) if ((act >> c) & 1u) needB |= 1u << (MODE == 0 ? c : 1 - c);
     if (diag) needA |= needB;
-    const int myc = NC == 2 ? (tid & 1) : 0;            // a thread always copies the same component
-    const bool ldA = (needA >> myc) & 1u, ldB = !diag && ((needB >> myc) & 1u);
 
     double acc[8][4][2];
 #pragma unroll
@@ -350,43 +349,56 @@ syrk_dmma2_kernel(const double* __restrict__ Xr, int64_t ldr, int64_t P, int64_t
 #pragma unroll
         for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
+    // copy coordinates of this thread: element e = tid + 256 i  ->  sample SPI*i + tid / (TS*NC), real row r
+    const int r = tid % (TS * NC), s_off = tid / (TS * NC);
+    const int myc = NC == 2 ? (r & 1) : 0;               // a thread always copies the same component
     const int64_t rowA = (int64_t)ti * TS * NC, rowB = (int64_t)tj * TS * NC, PR = P * NC;
-    // per-thread copy coordinates: e = tid + 256 i = s * (TS*NC) + r
+    // rows beyond P are never copied: their planes stay zero (zeroed below) and only feed padding outputs
+    const bool ldA = ((needA >> myc) & 1u) && rowA + r < PR, ldB = !diag && ((needB >> myc) & 1u) && rowB + r < PR;
+    const int dst0 = myc * PLQ + s_off * LDQ + r / NC;
+    const double* srcA = Xr + rowA + r + ldr * (c_begin * KS + s_off);
+    const double* srcB = Xr + rowB + r + ldr * (c_begin * KS + s_off);
+    const int64_t step = ldr * SPI;                      // doubles between two copies of this thread
+
     auto issue = [&](int64_t chunk, int stage) {
-        double* As = smem + stage * STG;
+        double* As = smem + stage * STG + dst0;
         double* Bs = As + TILE;
+        const int64_t smp0 = chunk * KS + s_off;
+        const double* pa = srcA + (chunk - c_begin) * KS * ldr;
+        const double* pb = srcB + (chunk - c_begin) * KS * ldr;
 #pragma unroll
         for (int i = 0; i < PER; i++) {
-            const int e = tid + 256 * i;
-            const int s = e / (TS * NC), r = e - s * (TS * NC);
-            const int64_t smp = chunk * KS + s;
-            const int dst = myc * PLQ + s * LDQ + r / NC;
-            if (ldA) { const bool ok = smp < Ns && rowA + r < PR; cp_async8(As + dst, Xr + (ok ? rowA + r + ldr * smp : 0), ok); }
-            if (ldB) { const bool ok = smp < Ns && rowB + r < PR; cp_async8(Bs + dst, Xr + (ok ? rowB + r + ldr * smp : 0), ok); }
+            const bool ok = smp0 + SPI * i < Ns;
+            if (ldA) cp_async8(As + SPI * i * LDQ, ok ? pa : Xr, ok);
+            if (ldB) cp_async8(Bs + SPI * i * LDQ, ok ? pb : Xr, ok);
+            pa += step; pb += step;
         }
     };
 
     if (act) {
+        for (int i = tid; i < NSTAGE * STG; i += 256) smem[i] = 0.0;
+        __syncthreads();
         const int64_t nch = c_end - c_begin;
 #pragma unroll
         for (int p = 0; p < NSTAGE - 1; p++) {
             if (p < nch) issue(c_begin + p, p);
             cp_async_commit();
         }
+        int stage = 0;
         for (int64_t it = 0; it < nch; it++) {
             cp_async_wait<NSTAGE - 2>();                // chunk `it` has landed (this thread's copies)
-            __syncthreads();                            // ... everyone's; and stage (it-1) % NSTAGE is free again
-            if (it + NSTAGE - 1 < nch) issue(c_begin + it + NSTAGE - 1, (int)((it + NSTAGE - 1) % NSTAGE));
+            __syncthreads();                            // ... everyone's; and the stage of chunk it-1 is free again
+            const int nstage = stage == 0 ? NSTAGE - 1 : stage - 1;     // (it + NSTAGE - 1) % NSTAGE
+            if (it + NSTAGE - 1 < nch) issue(c_begin + it + NSTAGE - 1, nstage);
             cp_async_commit();
-            const double* A = smem + (int)(it % NSTAGE) * STG;
+            const double* A = smem + stage * STG;
             const double* Bm = diag ? A : A + TILE;
 #pragma unroll
             for (int comp = 0; comp < NC; comp++) {
                 if (!((act >> comp) & 1u)) continue;
-                const int bcomp = mode == 0 ? comp : 1 - comp;
+                const int bcomp = MODE == 0 ? comp : 1 - comp;
                 const double* Ap = A + comp * PLQ + wm * 64 + g;
                 const double* Bp = Bm + bcomp * PLQ + wn * 32 + g;
-                const bool neg = mode == 1 && comp == 1;
 #pragma unroll
                 for (int k4 = 0; k4 < KS / 4; k4++) {
                     const int sidx = (4 * k4 + tq) * LDQ;
@@ -394,13 +406,14 @@ syrk_dmma2_kernel(const double* __restrict__ Xr, int64_t ldr, int64_t P, int64_t
 #pragma unroll
                     for (int i = 0; i < 8; i++) a[i] = Ap[sidx + i * 8];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) { double v = Bp[sidx + j * 8]; b[j] = neg ? -v : v; }
+                    for (int j = 0; j < 4; j++) { double v = Bp[sidx + j * 8]; b[j] = (MODE == 1 && comp == 1) ? -v : v; }
 #pragma unroll
                     for (int i = 0; i < 8; i++)
 #pragma unroll
                         for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                 }
             }
+            stage = stage == NSTAGE - 1 ? 0 : stage + 1;
         }
         cp_async_wait<0>();
     }
@@ -450,10 +463,16 @@ int launch_syrk(nq_ctx_t ctx, const void* X, int64_t ldr, int64_t P, int64_t Ns,
     dim3 grid((unsigned)(ntile * (ntile + 1) / 2), (unsigned)nsplit);
     static const bool old_path = [] { const char* e = getenv("NQ_SYRK_PATH"); return e && !strcmp(e, "staged"); }();
     if (sizeof(T) == 8 && !old_path) {
-        auto kern2 = syrk_dmma2_kernel<NC>;
         size_t smem2 = (size_t)NSTAGE * 2 * NC * PLQ * sizeof(double);
-        NQ_CUDA(ctx, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        NQ_LAUNCH(ctx, kern2, grid, 256, smem2, (const double*)X, ldr, P, Ns, ntile, nsplit, mode, (const unsigned*)flags, W);
+        if (mode == 0) {
+            auto kern2 = syrk_dmma2_kernel<NC, 0>;
+            NQ_CUDA(ctx, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            NQ_LAUNCH(ctx, kern2, grid, 256, smem2, (const double*)X, ldr, P, Ns, ntile, nsplit, (const unsigned*)flags, W);
+        } else {
+            auto kern2 = syrk_dmma2_kernel<NC, 1>;
+            NQ_CUDA(ctx, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            NQ_LAUNCH(ctx, kern2, grid, 256, smem2, (const double*)X, ldr, P, Ns, ntile, nsplit, (const unsigned*)flags, W);
+        }
         return NQ_OK;
     }
     auto kern = syrk_dmma_kernel<T, NC>;
