@@ -109,6 +109,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+NCU_FUSED_DRAM_BYTES = 4.5096e9   # local_ndm3s_kernel<double>, cfg4, 65536 configurations per launch
 FP64_TENSOR_PEAK = 37.2   # TFLOP/s, mma.sync m8n8k4 f64 at 8 warps/SM on this pool's B200 (profiles/fp64_peaks.json)
 
 
@@ -318,7 +319,9 @@ def run_gpu(args):
     bytes_fused = Ns * (2 * P * es + 2 * es + 2 * 8)      # O row + grad L_loc row + log rho + L_loc + packed words
     ach = bytes_fused / (t_loc * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "local_ndm3s_kernel<double,softplus,grad,with_O> (fused eval+grad+estimator)",
-            "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+            "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r1k_top_kernels.txt)
+            "traffic": NCU_FUSED_DRAM_BYTES if (world == 1 and Ns == 65536) else None,
             "peak_source": pk_kind, "ms_per_launch": t_loc, "algorithmic_bytes_per_launch": bytes_fused,
             "note": "the kernel is FP64-issue bound, not HBM bound: see DESIGN.md section 4",
             "all": {"ndm_evalgrad_kernel (stand-alone nq_logpsi_grad)": {
