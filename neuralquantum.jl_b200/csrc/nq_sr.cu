@@ -375,7 +375,65 @@ syrk_dmma2_kernel(const double* __restrict__ Xr, int64_t ldr, int64_t P, int64_t
         }
     };
 
-    if (act) {
+    // one active component (real-parameter NDM: purely real x purely real, imaginary x imaginary): the two
+    // planes of a stage hold 16 samples of that component, so a barrier still covers 128 DMMAs per warp
+    const bool single = NC == 2 && MODE == 0 && (act == 1u || act == 2u) && needA == act && (diag || needB == act);
+    if (single) {
+        const int comp = act == 1u ? 0 : 1;
+        for (int i = tid; i < NSTAGE * STG; i += 256) smem[i] = 0.0;
+        __syncthreads();
+        const int64_t smp_begin = c_begin * KS, smp_end = std::min<int64_t>(Ns, c_end * KS);
+        const int64_t nch = (smp_end - smp_begin + 2 * KS - 1) / (2 * KS);
+        const int m = tid & (TS - 1), sh = tid >> 7;                      // row of the tile, sample parity
+        const bool okA = rowA + 2 * m < PR, okB = !diag && rowB + 2 * m < PR;
+        const double* sA = Xr + rowA + 2 * m + comp + ldr * (smp_begin + sh);
+        const double* sB = Xr + rowB + 2 * m + comp + ldr * (smp_begin + sh);
+        auto issue1 = [&](int64_t ch, int stage) {
+            double* As = smem + stage * STG + sh * LDQ + m;
+            double* Bs = As + TILE;
+            const int64_t smp0 = smp_begin + ch * 2 * KS + sh;
+            const double* pa = sA + ch * 2 * KS * ldr;
+            const double* pb = sB + ch * 2 * KS * ldr;
+#pragma unroll
+            for (int i = 0; i < KS; i++) {
+                const bool ok = smp0 + 2 * i < smp_end;
+                if (okA) cp_async8(As + 2 * i * LDQ, ok ? pa : Xr, ok);
+                if (okB) cp_async8(Bs + 2 * i * LDQ, ok ? pb : Xr, ok);
+                pa += 2 * ldr; pb += 2 * ldr;
+            }
+        };
+#pragma unroll
+        for (int p = 0; p < NSTAGE - 1; p++) {
+            if (p < nch) issue1(p, p);
+            cp_async_commit();
+        }
+        int stage = 0;
+        for (int64_t it = 0; it < nch; it++) {
+            cp_async_wait<NSTAGE - 2>();
+            __syncthreads();
+            const int nstage = stage == 0 ? NSTAGE - 1 : stage - 1;
+            if (it + NSTAGE - 1 < nch) issue1(it + NSTAGE - 1, nstage);
+            cp_async_commit();
+            const double* A = smem + stage * STG;
+            const double* Ap = A + wm * 64 + g;
+            const double* Bp = (diag ? A : A + TILE) + wn * 32 + g;
+#pragma unroll
+            for (int k4 = 0; k4 < 2 * KS / 4; k4++) {
+                const int sidx = (4 * k4 + tq) * LDQ;
+                double a[8], b[4];
+#pragma unroll
+                for (int i = 0; i < 8; i++) a[i] = Ap[sidx + i * 8];
+#pragma unroll
+                for (int j = 0; j < 4; j++) b[j] = Bp[sidx + j * 8];
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+            stage = stage == NSTAGE - 1 ? 0 : stage + 1;
+        }
+        cp_async_wait<0>();
+    } else if (act) {
         for (int i = tid; i < NSTAGE * STG; i += 256) smem[i] = 0.0;
         __syncthreads();
         const int64_t nch = c_end - c_begin;
@@ -393,6 +451,24 @@ syrk_dmma2_kernel(const double* __restrict__ Xr, int64_t ldr, int64_t P, int64_t
             cp_async_commit();
             const double* A = smem + stage * STG;
             const double* Bm = diag ? A : A + TILE;
+            if (NC == 2 && MODE == 0 && act == 3u) {
+                // both components, same pairing on A and B: the two planes are just 16 rows of one K loop
+                const double* Ap = A + wm * 64 + g;
+                const double* Bp = Bm + wn * 32 + g;
+#pragma unroll
+                for (int k4 = 0; k4 < 2 * KS / 4; k4++) {
+                    const int sidx = (4 * k4 + tq) * LDQ;
+                    double a[8], b[4];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) a[i] = Ap[sidx + i * 8];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) b[j] = Bp[sidx + j * 8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                }
+            } else
 #pragma unroll
             for (int comp = 0; comp < NC; comp++) {
                 if (!((act >> comp) & 1u)) continue;
@@ -491,24 +567,36 @@ __device__ __forceinline__ cxd mulc(cxd a, cxd b) { return cxd(a.re * b.re + a.i
 __device__ __forceinline__ double divr(double a, double r) { return a / r; }
 __device__ __forceinline__ cxd divr(cxd a, double r) { return cxd(a.re / r, a.im / r); }
 
-// factor the diagonal block (held in shared memory Lb[NB][NB+1], row r = lane) with one warp
+__device__ __forceinline__ double lane_bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ cxd lane_bcast(cxd v, int src) { return cxd(__shfl_sync(0xffffffffu, v.re, src), __shfl_sync(0xffffffffu, v.im, src)); }
+
+// factor the diagonal block (shared memory Lb[NB][NB+1]) with one warp: lane r keeps row r in registers, the
+// pivot and the column below it travel by shuffles (right-looking, fully unrolled -- the shared-memory
+// read-modify-write version spent ~20 us per block on load/store round trips)
 template <typename E>
 __device__ void potf2_warp(E (*Lb)[NB + 1], int nb, int64_t j0, int* info) {
     const int r = threadIdx.x & 31;
-    for (int c = 0; c < nb; c++) {
-        double d = real_part(Lb[c][c]);
-        if (!(d > 0.0)) { if (r == 0) atomicCAS(info, -1, (int)(j0 + c)); d = 1.0; }
-        double l = sqrt(d);
-        __syncwarp();
-        if (r == c) Lb[c][c] = from_real<E, double>(l);
-        if (r > c && r < nb) Lb[r][c] = divr(Lb[r][c], l);
-        __syncwarp();
-        if (r > c && r < nb) {
-            E lrc = Lb[r][c];
-            for (int c2 = c + 1; c2 <= r; c2++) Lb[r][c2] -= mulc(lrc, Lb[c2][c]);
+    E row[NB];
+#pragma unroll
+    for (int c = 0; c < NB; c++) row[c] = Lb[r][c];
+#pragma unroll
+    for (int c = 0; c < NB; c++) {
+        double d = __shfl_sync(0xffffffffu, real_part(row[c]), c);
+        if (c >= nb) d = 1.0;
+        else if (!(d > 0.0)) { if (r == 0) atomicCAS(info, -1, (int)(j0 + c)); d = 1.0; }
+        const double l = sqrt(d);
+        if (r == c) row[c] = from_real<E, double>(l);
+        else if (r > c) row[c] = divr(row[c], l);
+        const E lrc = row[c];
+#pragma unroll
+        for (int c2 = c + 1; c2 < NB; c2++) {
+            const E t = lane_bcast(lrc, c2);            // L[c2][c]
+            if (r >= c2) row[c2] -= mulc(lrc, t);
         }
-        __syncwarp();
     }
+#pragma unroll
+    for (int c = 0; c < NB; c++) Lb[r][c] = row[c];
+    __syncwarp();
 }
 
 // panel: every CTA factors the diagonal block redundantly in shared memory; CTA 0 writes it back;
