@@ -298,6 +298,28 @@ __device__ __forceinline__ void ratio_step(E s, E Ep, E Em, E& fac, E& snew) {
         snew = e_div(a - b, sum);
     }
 }
+NQ_HD double abs2_d(float a) { return (double)a * (double)a; }
+NQ_HD double abs2_d(double a) { return a * a; }
+template <typename T> NQ_HD double abs2_d(cx<T> a) { return (double)a.re * (double)a.re + (double)a.im * (double)a.im; }
+// same step with the division deferred: snew = e_div(num, den) (bit-identical to ratio_step); the sampler only
+// divides for accepted proposals.  den follows from fac (softplus: fac; logcosh: 2 fac, exact).
+template <int ACT, typename E>
+__device__ __forceinline__ void ratio_parts(E s, E Ep, E Em, E& fac, E& num) {
+    typedef typename elem_traits<E>::real T;
+    if (ACT == NQ_SOFTPLUS) {
+        fac = e_one<E>() + e_mul(s, Ep - e_one<E>());
+        num = e_mul(s, Ep);
+    } else {
+        E a = e_mul(Ep, e_one<E>() + s), b = e_mul(Em, e_one<E>() - s);
+        fac = rscale(T(0.5), a + b);
+        num = a - b;
+    }
+}
+template <int ACT, typename E>
+__device__ __forceinline__ E ratio_finish(E fac, E num) {
+    typedef typename elem_traits<E>::real T;
+    return e_div(num, ACT == NQ_SOFTPLUS ? fac : rscale(T(2), fac));
+}
 // products are accumulated in double precision whatever the mode
 NQ_HD double to_d(float a) { return (double)a; }
 NQ_HD double to_d(double a) { return a; }

@@ -102,6 +102,22 @@ __device__ __forceinline__ void draw(const RunArgs& a, int64_t chain, uint64_t p
     }
 }
 
+// Proposal ps of a stored step: the 32 lanes generate the (site, uniform) pairs of 32 consecutive proposals at
+// once (lane l -> proposal ps0 + l; same Philox counters as one call per proposal) and every proposal reads
+// its pair with shuffles.  Replay mode reads the caller's arrays.
+template <typename T>
+struct DrawBatch {
+    int site_l; T u_l;
+    __device__ __forceinline__ void fill(const RunArgs& a, int64_t chain, int pic0, int nleft, int nsites, int lane) {
+        site_l = 0; u_l = T(0);
+        if (lane < nleft) draw<T>(a, chain, a.pass_base + (uint64_t)(pic0 + lane), pic0 + lane, nsites, site_l, u_l);
+    }
+    __device__ __forceinline__ void get(int idx, int& site, T& u) const {
+        site = __shfl_sync(0xffffffffu, site_l, idx);
+        u = __shfl_sync(0xffffffffu, u_l, idx);
+    }
+};
+
 // ---- RBM / RBMSplit -------------------------------------------------------------------
 // Per chain (warp) only s_k = f'(theta_k) is tracked: with the per-parameter tables Ep = exp(+-c W_kj) a
 // proposal costs one table load, a few multiply-adds and one division per hidden unit -- no transcendental --
@@ -115,11 +131,19 @@ __global__ void sampler_rbm_kernel(const E* __restrict__ par, const E* __restric
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int64_t chain = blockIdx.x * (int64_t)wpb + warp;
-    if (chain >= a.B) return;
     const int N = a.N, M = a.M, W64 = (N + 63) >> 6;
-    E* sk = (E*)smem_raw + (size_t)warp * 2 * M;
-    E* ts = sk + M;
     const int64_t off_b = DOUBLED ? 2 * N : N;
+    // eb[(sign * nmat + mat) * N + j] = |exp(dv a_j)|^2 for the two possible flips of site j (CTA-wide table)
+    T* eb = (T*)smem_raw;
+    for (int i = threadIdx.x; i < 2 * (DOUBLED ? 2 : 1) * N; i += blockDim.x) {
+        const int nm = DOUBLED ? 2 : 1, sgn = i / (nm * N), rem = i - sgn * nm * N, mt = rem / N, jj = rem - mt * N;
+        const T dvv = a.hilb == NQ_SPIN ? (sgn ? T(-2) : T(2)) : (sgn ? T(-1) : T(1));
+        eb[i] = (T)abs2_d(e_exp(rscale(dvv, par[(mt ? N : 0) + jj])));
+    }
+    __syncthreads();
+    if (chain >= a.B) return;
+    E* sk = (E*)(smem_raw + ((size_t)4 * N * sizeof(T) + 15) / 16 * 16) + (size_t)warp * 3 * M;
+    E* ts = sk + M;               // [2M]: numerators, then factors
     const E* __restrict__ Wr = par + off_b + M;
     const E* __restrict__ Wc = Wr + (int64_t)M * N;
     const int64_t MN = (int64_t)M * N;
@@ -145,31 +169,34 @@ __global__ void sampler_rbm_kernel(const E* __restrict__ par, const E* __restric
             sk[k] = d;
         }
         __syncwarp();
+        DrawBatch<T> db;
 #pragma unroll 1
         for (int ps = 0; ps < a.passes; ps++) {
             int pic = step * a.passes + ps;
+            if ((ps & 31) == 0) db.fill(a, chain, pic, a.passes - ps, nsites, lane);
             int site; T u;
-            draw<T>(a, chain, a.pass_base + (uint64_t)pic, pic, nsites, site, u);
+            db.get(ps & 31, site, u);
             const bool col = DOUBLED && site >= N;
             const int j = col ? site - N : site;
             const T dv = flip_delta<T>(a.hilb, get_bit(col ? cb : rb, j));
             const int sg = dv > T(0) ? 0 : 1, mat = col ? 1 : 0;
             const E* __restrict__ tp = tab + (int64_t)(sg * nmat + mat) * MN + (int64_t)M * j;
             const E* __restrict__ tm = tab + (int64_t)((1 - sg) * nmat + mat) * MN + (int64_t)M * j;
-            PD prod = to_d(e_one<E>());
+            // |psi(eta)/psi(sigma)|^2 = |e^{a_j dv}|^2 prod_k |fac_k|^2: one real product; the new s_k = num / den
+            // is only formed when the move is accepted
+            double prod = 1.0;
             for (int k = lane; k < M; k += 32) {
                 E Ep = tp[k], Em = ACT == NQ_LOGCOSH ? tm[k] : e_one<E>();
-                E fac, sn;
-                ratio_step<ACT>(sk[k], Ep, Em, fac, sn);
-                prod = prod * to_d(fac);
-                ts[k] = sn;
+                E fac, num;
+                ratio_parts<ACT>(sk[k], Ep, Em, fac, num);
+                prod *= abs2_d(fac);
+                ts[k] = num; ts[M + k] = fac;
             }
             prod = warp_prod(prod);
-            const PD ratio = prod * to_d(e_exp(rscale(dv, par[(col ? N : 0) + j])));
-            const double pr = to_d(real_part(ratio)) * to_d(real_part(ratio)) + to_d(imag_part(ratio)) * to_d(imag_part(ratio));
+            const double pr = prod * (double)eb[(sg * nmat + mat) * N + j];
             const bool acc = (u - (T)pr) < T(0);
             if (acc) {
-                for (int k = lane; k < M; k += 32) sk[k] = ts[k];
+                for (int k = lane; k < M; k += 32) sk[k] = ratio_finish<ACT>(ts[M + k], ts[k]);
                 if (col) cb[j >> 6] ^= 1ull << (j & 63); else rb[j >> 6] ^= 1ull << (j & 63);
                 nacc++;
             }
@@ -198,17 +225,25 @@ __global__ void sampler_ndm_kernel(const T* __restrict__ par, const T* __restric
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int64_t chain = blockIdx.x * (int64_t)wpb + warp;
-    if (chain >= a.B) return;
     const int N = a.N, M = a.M, A = a.A, W64 = (N + 63) >> 6;
-    const size_t per_warp = (size_t)(3 * M) * sizeof(T) + (size_t)(2 * A) * sizeof(C);
-    unsigned char* base = smem_raw + (size_t)warp * ((per_warp + 15) / 16 * 16);
-    C* spi = (C*)base;            // [A]
-    C* tspi = spi + A;
-    T* sl = (T*)(tspi + A);       // [2M]
-    T* tsl = sl + 2 * M;          // [M]
     const int64_t MN = (int64_t)M * N, AN = (int64_t)A * N;
     const int64_t o_wmu = N + M, o_umu = o_wmu + MN, o_blam = o_umu + AN,
                   o_hlam = o_blam + N, o_dlam = o_hlam + M, o_wlam = o_dlam + A, o_ulam = o_wlam + MN;
+    // eb[sign * N + j] = exp(dv b_lam_j) for the two possible flips of site j (CTA-wide table)
+    T* eb = (T*)smem_raw;
+    for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) {
+        const int sgn = i / N, jj = i - sgn * N;
+        const T dvv = a.hilb == NQ_SPIN ? (sgn ? T(-2) : T(2)) : (sgn ? T(-1) : T(1));
+        eb[i] = (T)exp((double)(dvv * par[o_blam + jj]));
+    }
+    __syncthreads();
+    if (chain >= a.B) return;
+    const size_t per_warp = (size_t)(4 * M) * sizeof(T) + (size_t)(3 * A) * sizeof(C);
+    unsigned char* base = smem_raw + ((size_t)2 * N * sizeof(T) + 15) / 16 * 16 + (size_t)warp * ((per_warp + 15) / 16 * 16);
+    C* spi = (C*)base;            // [A]
+    C* tspi = spi + A;            // [2A]: numerators, then factors
+    T* sl = (T*)(tspi + 2 * A);   // [2M]
+    T* tsl = sl + 2 * M;          // [2M]: numerators, then factors
     const T half = T(0.5);
     uint64_t rb[MAXW], cb[MAXW];
 #pragma unroll
@@ -244,11 +279,13 @@ __global__ void sampler_ndm_kernel(const T* __restrict__ par, const T* __restric
             spi[q] = d;
         }
         __syncwarp();
+        DrawBatch<T> db;
 #pragma unroll 1
         for (int ps = 0; ps < a.passes; ps++) {
             int pic = step * a.passes + ps;
+            if ((ps & 31) == 0) db.fill(a, chain, pic, a.passes - ps, 2 * N, lane);
             int site; T u;
-            draw<T>(a, chain, a.pass_base + (uint64_t)pic, pic, 2 * N, site, u);
+            db.get(ps & 31, site, u);
             const bool col = site >= N;
             const int j = col ? site - N : site;
             const T dv = flip_delta<T>(a.hilb, get_bit(col ? cb : rb, j));
@@ -258,30 +295,30 @@ __global__ void sampler_ndm_kernel(const T* __restrict__ par, const T* __restric
             const T* __restrict__ tm = tabr + (int64_t)(1 - sg) * 2 * MN + (int64_t)M * j;
             const C* __restrict__ cp = tabc + (int64_t)sg * AN + (int64_t)A * j;
             const C* __restrict__ cm = tabc + (int64_t)(1 - sg) * AN + (int64_t)A * j;
+            // |rho(eta)/rho(sigma)|^2 = e^{b_lam dv} prod_k fac_k prod_q |fac_q|^2: ONE real product; the new
+            // f' values (num / den) are only formed when the move is accepted
             double pl = 1.0;
-            cxd pp(1.0, 0.0);
             for (int k = lane; k < M; k += 32) {
                 T Ep = tp[k], Em = ACT == NQ_LOGCOSH ? tm[k] : T(1);
-                T fac, sn;
-                ratio_step<ACT>(sl[so + k], Ep, Em, fac, sn);
+                T fac, num;
+                ratio_parts<ACT>(sl[so + k], Ep, Em, fac, num);
                 pl *= (double)fac;
-                tsl[k] = sn;
+                tsl[k] = num; tsl[M + k] = fac;
             }
             for (int q = lane; q < A; q += 32) {
                 C Ep = cp[q], Em = ACT == NQ_LOGCOSH ? cm[q] : C(T(1), T(0));
                 if (col) { Ep.im = -Ep.im; Em.im = -Em.im; }
-                C fac, sn;
-                ratio_step<ACT>(spi[q], Ep, Em, fac, sn);
-                pp = pp * to_d(fac);
-                tspi[q] = sn;
+                C fac, num;
+                ratio_parts<ACT>(spi[q], Ep, Em, fac, num);
+                pl *= abs2_d(fac);
+                tspi[q] = num; tspi[A + q] = fac;
             }
             pl = warp_prod(pl);
-            pp = warp_prod(pp);
-            const double pr = pl * exp((double)(dv * par[o_blam + j])) * (pp.re * pp.re + pp.im * pp.im);
+            const double pr = pl * (double)eb[sg * N + j];
             const bool acc = (u - (T)pr) < T(0);
             if (acc) {
-                for (int k = lane; k < M; k += 32) sl[so + k] = tsl[k];
-                for (int q = lane; q < A; q += 32) spi[q] = tspi[q];
+                for (int k = lane; k < M; k += 32) sl[so + k] = ratio_finish<ACT>(tsl[M + k], tsl[k]);
+                for (int q = lane; q < A; q += 32) spi[q] = ratio_finish<ACT>(tspi[A + q], tspi[q]);
                 if (col) cb[j >> 6] ^= 1ull << (j & 63); else rb[j >> 6] ^= 1ull << (j & 63);
                 nacc++;
             }
@@ -303,10 +340,11 @@ template <typename E, int ACT, bool DOUBLED>
 int launch_sampler_rbm(nq_sampler_t s, const RunArgs& a) {
     nq_machine_t m = s->m;
     nq_ctx_t ctx = m->ctx;
-    size_t per_warp = (size_t)2 * m->M * sizeof(E);
+    size_t per_warp = (size_t)3 * m->M * sizeof(E);
+    const size_t tab_bytes = ((size_t)4 * m->N * sizeof(typename elem_traits<E>::real) + 15) / 16 * 16;
     int wpb = 8;
     while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
-    size_t smem = per_warp * wpb;
+    size_t smem = tab_bytes + per_warp * wpb;
     if (smem > ctx->smem_optin) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "sampler needs %zu B shared memory per chain", per_warp);
     auto kern = sampler_rbm_kernel<E, ACT, DOUBLED>;
     NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -319,11 +357,12 @@ template <typename T, int ACT>
 int launch_sampler_ndm(nq_sampler_t s, const RunArgs& a) {
     nq_machine_t m = s->m;
     nq_ctx_t ctx = m->ctx;
-    size_t per_warp = ((size_t)3 * m->M * sizeof(T) + (size_t)2 * m->A * sizeof(cx<T>) + 15) / 16 * 16;
+    size_t per_warp = ((size_t)4 * m->M * sizeof(T) + (size_t)3 * m->A * sizeof(cx<T>) + 15) / 16 * 16;
+    const size_t tab_bytes = ((size_t)2 * m->N * sizeof(T) + 15) / 16 * 16;
     const cx<T>* tabc = (const cx<T>*)((const char*)m->etab + ((size_t)4 * m->M * m->N * sizeof(T) + 15) / 16 * 16);
     int wpb = 8;
     while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
-    size_t smem = per_warp * wpb;
+    size_t smem = tab_bytes + per_warp * wpb;
     if (smem > ctx->smem_optin) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "sampler needs %zu B shared memory per chain", per_warp);
     auto kern = sampler_ndm_kernel<T, ACT>;
     NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
