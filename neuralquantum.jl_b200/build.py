@@ -47,6 +47,9 @@ def build(force=False, verbose=False):
     hdrs = (glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inc")) +
             glob.glob(os.path.join(HERE, "..", "include", "*.h")))
     inc = ["-I", _nccl_include()]
+    # the linked library is newer than every source: nothing to do (object files do not travel to the GPU box)
+    if not force and os.path.exists(LIB) and not _stale(LIB, srcs + hdrs):
+        return LIB
     jobs = []
     for s in srcs:
         o = os.path.join(BUILD, os.path.basename(s)[:-3] + ".o")

@@ -574,7 +574,7 @@ __device__ __forceinline__ cxd lane_bcast(cxd v, int src) { return cxd(__shfl_sy
 // pivot and the column below it travel by shuffles (right-looking, fully unrolled -- the shared-memory
 // read-modify-write version spent ~20 us per block on load/store round trips)
 template <typename E>
-__device__ void potf2_warp(E (*Lb)[NB + 1], int nb, int64_t j0, int* info) {
+__device__ void potf2_warp(E (*Lb)[NB + 1], double* Dinv, int nb, int64_t j0, int* info) {
     const int r = threadIdx.x & 31;
     E row[NB];
 #pragma unroll
@@ -584,9 +584,11 @@ __device__ void potf2_warp(E (*Lb)[NB + 1], int nb, int64_t j0, int* info) {
         double d = __shfl_sync(0xffffffffu, real_part(row[c]), c);
         if (c >= nb) d = 1.0;
         else if (!(d > 0.0)) { if (r == 0) atomicCAS(info, -1, (int)(j0 + c)); d = 1.0; }
-        const double l = sqrt(d);
-        if (r == c) row[c] = from_real<E, double>(l);
-        else if (r > c) row[c] = divr(row[c], l);
+        // the pivot chain is the critical path of the whole factorisation: reciprocal square root + multiplies
+        // instead of sqrt + divisions (1/l is kept for the TRSM rows and the triangular solves)
+        const double inv = rsqrt(d);
+        if (r == c) { row[c] = from_real<E, double>(d * inv); Dinv[c] = inv; }
+        else if (r > c) row[c] = rscale(inv, row[c]);
         const E lrc = row[c];
 #pragma unroll
         for (int c2 = c + 1; c2 < NB; c2++) {
@@ -604,13 +606,14 @@ __device__ void potf2_warp(E (*Lb)[NB + 1], int nb, int64_t j0, int* info) {
 template <typename E>
 __global__ void chol_panel_kernel(E* __restrict__ A, int64_t P, int64_t j0, int nb, int* __restrict__ info) {
     __shared__ E Lb[NB][NB + 1];
+    __shared__ double Dinv[NB];
     const int tid = threadIdx.x;
     for (int i = tid; i < NB * NB; i += blockDim.x) {
         int r = i % NB, c = i / NB;
         Lb[r][c] = (r < nb && c < nb && c <= r) ? A[(j0 + r) + P * (j0 + c)] : make_zero<E>();
     }
     __syncthreads();
-    if (tid < 32) potf2_warp<E>(Lb, nb, j0, info);
+    if (tid < 32) potf2_warp<E>(Lb, Dinv, nb, j0, info);
     __syncthreads();
     if (blockIdx.x == 0) {
         for (int i = tid; i < NB * NB; i += blockDim.x) {
@@ -629,7 +632,7 @@ __global__ void chol_panel_kernel(E* __restrict__ A, int64_t P, int64_t j0, int 
             E v = x[c];
 #pragma unroll
             for (int c2 = 0; c2 < NB; c2++) if (c2 < c) v -= mulc(x[c2], Lb[c][c2]);
-            x[c] = divr(v, real_part(Lb[c][c]));
+            x[c] = rscale(Dinv[c], v);
         }
     }
 #pragma unroll
@@ -707,8 +710,9 @@ __global__ void __launch_bounds__(512) chol_solve_kernel(const E* __restrict__ L
         __syncthreads();
         if (warp == 0) {
             E v = lane < nb ? x[j0 + lane] : make_zero<E>();
+            const double dinv = lane < nb ? 1.0 / real_part(Lb[lane][lane]) : 1.0;     // off the serial chain
             for (int c = 0; c < nb; c++) {
-                E yc = divr(bcast(v, c), real_part(Lb[c][c]));
+                E yc = rscale(__shfl_sync(0xffffffffu, dinv, c), lane_bcast(v, c));
                 if (lane == c) v = yc;
                 if (lane > c && lane < nb) v -= Lb[lane][c] * yc;
             }
@@ -740,8 +744,9 @@ __global__ void __launch_bounds__(512) chol_solve_kernel(const E* __restrict__ L
         __syncthreads();
         if (warp == 0) {
             E v = lane < nb ? blk[lane] : make_zero<E>();
+            const double dinv = lane < nb ? 1.0 / real_part(Lb[lane][lane]) : 1.0;
             for (int c = nb - 1; c >= 0; c--) {
-                E xc = divr(bcast(v, c), real_part(Lb[c][c]));
+                E xc = rscale(__shfl_sync(0xffffffffu, dinv, c), lane_bcast(v, c));
                 if (lane == c) v = xc;
                 if (lane < c) v -= mulc(xc, Lb[c][lane]);   // conj(L[c][lane]) x_c
             }
