@@ -694,6 +694,92 @@ template <typename E> __device__ __forceinline__ E bcast(E v, int src) {
     return mk<E>(__shfl_sync(0xffffffffu, real_part(v), src), __shfl_sync(0xffffffffu, imag_part(v), src));
 }
 
+// trailing update on the FP64 tensor pipe: A[i,l] -= sum_c X[i,c] conj(X[l,c]) for the lower 64x64 tiles, K = nb <= 32.
+// Panel rows staged as planar (re | im) [c][row] with pitch 68 (conflict-free fragment loads); 8 warps as
+// 2 (rows) x 4 (cols), warp tile 32x16 = 4x2 mma tiles; complex: re = rr + ii, im = ir - ri.
+constexpr int LDU = 64 + 4;
+template <typename E>
+__global__ void __launch_bounds__(256) chol_update_dmma_kernel(E* __restrict__ A, int64_t P, int64_t j0, int nb) {
+    constexpr bool CPLX = sizeof(E) == 16;
+    constexpr int NPL = CPLX ? 2 : 1;
+    extern __shared__ __align__(16) double usm[];
+    double* Xi = usm;                          // [NPL][NB][LDU]
+    double* Xl = usm + NPL * NB * LDU;
+    int t = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+    while (ti * (ti + 1) / 2 > t) ti--;
+    const int tj = t - ti * (ti + 1) / 2;
+    const bool diag = ti == tj;
+    const int64_t base = j0 + nb;
+    const int64_t i0 = base + (int64_t)ti * 64, l0 = base + (int64_t)tj * 64;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tq = lane & 3, wm = warp & 1, wn = warp >> 1;
+    const double* Ad = reinterpret_cast<const double*>(A);
+    for (int e = tid; e < NB * 64; e += 256) {
+        const int r = e & 63, c = e >> 6;
+        const bool okc = c < nb;
+        {
+            const bool ok = okc && i0 + r < P;
+            const int64_t at = (i0 + r) + P * (j0 + c);
+            Xi[c * LDU + r] = ok ? Ad[at * NPL] : 0.0;
+            if (CPLX) Xi[(NB + c) * LDU + r] = ok ? Ad[at * NPL + 1] : 0.0;
+        }
+        if (!diag) {
+            const bool ok = okc && l0 + r < P;
+            const int64_t at = (l0 + r) + P * (j0 + c);
+            Xl[c * LDU + r] = ok ? Ad[at * NPL] : 0.0;
+            if (CPLX) Xl[(NB + c) * LDU + r] = ok ? Ad[at * NPL + 1] : 0.0;
+        }
+    }
+    __syncthreads();
+    const double* Bq = diag ? Xi : Xl;
+    double cre[4][2][2], cim[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) { cre[i][j][0] = cre[i][j][1] = 0.0; cim[i][j][0] = cim[i][j][1] = 0.0; }
+    const double* Ap = Xi + wm * 32 + g;
+    const double* Bp = Bq + wn * 16 + g;
+#pragma unroll
+    for (int k4 = 0; k4 < NB / 4; k4++) {
+        const int sidx = (4 * k4 + tq) * LDU;
+        double ar[4], ai[4], br[2], bi[2], nbi[2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { ar[i] = Ap[sidx + i * 8]; if (CPLX) ai[i] = Ap[NB * LDU + sidx + i * 8]; }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            br[j] = Bp[sidx + j * 8];
+            if (CPLX) { bi[j] = Bp[NB * LDU + sidx + j * 8]; nbi[j] = -bi[j]; }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                dmma(cre[i][j][0], cre[i][j][1], ar[i], br[j]);
+                if (CPLX) {
+                    dmma(cre[i][j][0], cre[i][j][1], ai[i], bi[j]);
+                    dmma(cim[i][j][0], cim[i][j][1], ai[i], br[j]);
+                    dmma(cim[i][j][0], cim[i][j][1], ar[i], nbi[j]);
+                }
+            }
+    }
+    double* Aw = reinterpret_cast<double*>(A);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int64_t row = i0 + wm * 32 + i * 8 + g, col = l0 + wn * 16 + j * 8 + 2 * tq + h;
+                if (row < P && col < P && row >= col) {
+                    const int64_t at = (row + P * col) * NPL;
+                    Aw[at] -= cre[i][j][h];
+                    if (CPLX) Aw[at + 1] -= cim[i][j][h];
+                }
+            }
+}
+
 // forward L y = b (right-looking, coalesced row updates) then backward L^H x = y (left-looking,
 // coalesced column dot products); a single CTA walks the block columns.
 template <typename E>
@@ -756,6 +842,62 @@ __global__ void __launch_bounds__(512) chol_solve_kernel(const E* __restrict__ L
     }
 }
 
+// Multi-CTA triangular solves, one launch per block column.  Every CTA solves the 32x32 diagonal system
+// redundantly (reciprocal diagonals, ~3 us) and then updates its share of the remaining right-hand side:
+//   FWD  L y = b:    y_blk = L_jj^{-1} b_blk;   b[i] -= L[i, blk] y_blk        for the rows i below the block
+//   BWD  L^H x = y:  x_blk = L_jj^{-H} y_blk;   y[k] -= conj(L[blk, k])^T x_blk  for the columns k before it
+// The block result goes to a separate vector (other CTAs still read the block of the right-hand side).
+template <typename E, bool FWD>
+__global__ void __launch_bounds__(256) chol_trsv_step_kernel(const E* __restrict__ L, int64_t P, int64_t j0, int nb,
+                                                             E* __restrict__ rhs, E* __restrict__ out) {
+    __shared__ E Lb[NB][NB + 1];
+    __shared__ E xb[NB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < NB * NB; i += 256) {
+        int r = i % NB, c = i / NB;
+        Lb[r][c] = (r < nb && c < nb && c <= r) ? L[(j0 + r) + P * (j0 + c)] : make_zero<E>();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        E v = lane < nb ? rhs[j0 + lane] : make_zero<E>();
+        const double dinv = lane < nb ? 1.0 / real_part(Lb[lane][lane]) : 1.0;
+        if (FWD) {
+            for (int c = 0; c < nb; c++) {
+                E yc = rscale(__shfl_sync(0xffffffffu, dinv, c), lane_bcast(v, c));
+                if (lane == c) v = yc;
+                if (lane > c && lane < nb) v -= Lb[lane][c] * yc;
+            }
+        } else {
+            for (int c = nb - 1; c >= 0; c--) {
+                E xc = rscale(__shfl_sync(0xffffffffu, dinv, c), lane_bcast(v, c));
+                if (lane == c) v = xc;
+                if (lane < c) v -= mulc(xc, Lb[c][lane]);   // conj(L[c][lane]) x_c
+            }
+        }
+        xb[lane] = lane < nb ? v : make_zero<E>();
+        if (blockIdx.x == 0 && lane < nb) out[j0 + lane] = v;
+    }
+    __syncthreads();
+    if (FWD) {
+        const int64_t i = j0 + nb + blockIdx.x * 256 + tid;
+        if (i < P) {
+            E v = rhs[i];
+#pragma unroll 8
+            for (int c = 0; c < NB; c++) if (c < nb) v -= L[i + P * (j0 + c)] * xb[c];
+            rhs[i] = v;
+        }
+    } else {
+        const int64_t k = blockIdx.x * 256 + tid;
+        if (k < j0) {
+            E v = rhs[k];
+            const E* col = L + j0 + P * k;
+#pragma unroll 8
+            for (int r = 0; r < NB; r++) if (r < nb) v -= mulc(xb[r], col[r]);     // conj(L[j0+r, k]) x_r
+            rhs[k] = v;
+        }
+    }
+}
+
 template <typename E>
 __global__ void add_diag_kernel(E* __restrict__ A, int64_t P, double eps) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -771,10 +913,39 @@ int cholesky_solve(nq_ctx_t ctx, E* A, int64_t P, E* x, int* dinfo) {
         NQ_LAUNCH(ctx, chol_panel_kernel<E>, gp, 128, 0, A, P, j0, nb, dinfo);
         if (below > 0) {
             int64_t nt = (below + 63) / 64;
-            NQ_LAUNCH(ctx, chol_update_kernel<E>, (unsigned)(nt * (nt + 1) / 2), 256, 0, A, P, j0, nb);
+            static const bool scalar_update = [] { const char* e = getenv("NQ_CHOL_UPDATE"); return e && !strcmp(e, "scalar"); }();
+            if (scalar_update) {
+                NQ_LAUNCH(ctx, chol_update_kernel<E>, (unsigned)(nt * (nt + 1) / 2), 256, 0, A, P, j0, nb);
+            } else {
+                const size_t usmem = (size_t)2 * (sizeof(E) / 8) * NB * LDU * sizeof(double);
+                auto ku = chol_update_dmma_kernel<E>;
+                if (j0 == 0) NQ_CUDA(ctx, cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
+                NQ_LAUNCH(ctx, ku, (unsigned)(nt * (nt + 1) / 2), 256, usmem, A, P, j0, nb);
+            }
         }
     }
-    NQ_LAUNCH(ctx, chol_solve_kernel<E>, 1, 512, 0, (const E*)A, P, x);
+    static const bool single_cta = [] { const char* e = getenv("NQ_CHOL_TRSV"); return e && !strcmp(e, "single"); }();
+    // one CTA streams L twice (time ~ P^2, latency-bound per block); per-block launches cost ~7 us each (time ~ P):
+    // measured crossover near P = 2500 doubles (cfg4, P = 2176: 0.6 ms single vs 1.0 ms; cfg3, P = 5364 complex: 20.8 vs 6 ms)
+    if (single_cta || P * (int64_t)(sizeof(E) / 8) <= 3000) {
+        NQ_LAUNCH(ctx, chol_solve_kernel<E>, 1, 512, 0, (const E*)A, P, x);
+        return NQ_OK;
+    }
+    E* W = (E*)nq_scratch(ctx, SL_W2, (size_t)2 * P * sizeof(E));
+    if (!W) return NQ_ERR_ALLOC;
+    E* y = W;
+    E* xo = W + P;
+    for (int64_t j0 = 0; j0 < P; j0 += NB) {
+        int nb = (int)std::min<int64_t>(NB, P - j0);
+        unsigned g = (unsigned)std::max<int64_t>(1, (P - j0 - nb + 255) / 256);
+        NQ_LAUNCH(ctx, (chol_trsv_step_kernel<E, true>), g, 256, 0, (const E*)A, P, j0, nb, x, y);
+    }
+    for (int64_t j0 = ((P - 1) / NB) * NB; j0 >= 0; j0 -= NB) {
+        int nb = (int)std::min<int64_t>(NB, P - j0);
+        unsigned g = (unsigned)std::max<int64_t>(1, (j0 + 255) / 256);
+        NQ_LAUNCH(ctx, (chol_trsv_step_kernel<E, false>), g, 256, 0, (const E*)A, P, j0, nb, y, xo);
+    }
+    NQ_CUDA(ctx, cudaMemcpyAsync(x, xo, (size_t)P * sizeof(E), cudaMemcpyDeviceToDevice, ctx->stream));
     return NQ_OK;
 }
 
