@@ -141,6 +141,26 @@ def test_cholesky_and_cg_solve(nq, ctx, P, cplx):
             assert abs(its.value - it_ref) <= 2          # same stopping rule as the oracle (unpinned in the reference)
 
 
+@pytest.mark.parametrize("P,cplx", [(1700, True), (3200, False)])
+def test_cholesky_large_systems(nq, ctx, P, cplx):
+    """Large systems take the DMMA trailing update and the multi-CTA per-block triangular solves."""
+    import ctypes as C
+    L = nq._lib
+    rng = np.random.default_rng(17)
+    X = rng.standard_normal((P, 2 * P)) + (1j * rng.standard_normal((P, 2 * P)) if cplx else 0)
+    S = np.asfortranarray((X @ X.conj().T) / (2 * P))
+    F = rng.standard_normal(P) + (1j * rng.standard_normal(P) if cplx else 0)
+    eps = OSR.eps_f32(0.001)
+    ref = np.linalg.solve(S + eps * np.eye(P), F)
+    dw = np.zeros_like(F)
+    its = C.c_int64()
+    Sw = S.copy(order="F")               # keep the buffer alive across the call (L.ptr does not hold a reference)
+    L.check(L.lib.nq_sr_solve(ctx.h, L.ptr(Sw), L.ptr(F), P, L.NQ_C128 if cplx else L.NQ_F64, eps,
+                              L.NQ_SOLVE_CHOLESKY, 1e-12, 0, L.ptr(dw), C.byref(its)), ctx.h)
+    cond = np.linalg.cond(S + eps * np.eye(P))
+    assert np.linalg.norm(dw - ref) <= max(1e-10, 1e-14 * cond) * np.linalg.norm(ref)
+
+
 def test_cholesky_not_posdef_and_cg_not_converged(nq, ctx):
     import ctypes as C
     L = nq._lib
