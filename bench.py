@@ -159,6 +159,9 @@ class ClockSampler:
 
 
 def run_gpu(args):
+    # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     import nqcuda as nq
