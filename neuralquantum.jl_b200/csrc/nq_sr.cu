@@ -173,6 +173,36 @@ __global__ void tile_activity_kernel(const T* __restrict__ Xr, int64_t ldr, int6
     if (nz) atomicOr(&flags[(r / NC) / TS], 1u << (r % NC));
 }
 
+// tiles of the lower triangle sorted by work (number of active component pairs, descending; stable): the
+// last CTAs of the grid are then the cheap ones and the tail of the launch is short
+__global__ void tile_order_kernel(const unsigned* __restrict__ flags, int ntile, int mode, int* __restrict__ order) {
+    __shared__ int cnt[256][3];
+    const int ntri = ntile * (ntile + 1) / 2, tid = threadIdx.x;
+    const int per = (ntri + 255) / 256, lo = min(ntri, tid * per), hi = min(ntri, lo + per);
+    auto weight = [&](int t) {
+        int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+        while (ti * (ti + 1) / 2 > t) ti--;
+        const int tj = t - ti * (ti + 1) / 2;
+        const unsigned fa = flags[ti], fb = flags[tj];
+        int w = 0;
+        for (int c = 0; c < 2; c++) { const int bc = mode == 0 ? c : 1 - c; w += ((fa >> c) & 1u) && ((fb >> bc) & 1u); }
+        return w;
+    };
+    int c0 = 0, c1 = 0, c2 = 0;
+    for (int t = lo; t < hi; t++) { const int w = weight(t); c0 += w == 0; c1 += w == 1; c2 += w == 2; }
+    cnt[tid][0] = c0; cnt[tid][1] = c1; cnt[tid][2] = c2;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int w = 2; w >= 0; w--)
+            for (int i = 0; i < 256; i++) { const int c = cnt[i][w]; cnt[i][w] = run; run += c; }
+    }
+    __syncthreads();
+    int p[3] = {cnt[tid][0], cnt[tid][1], cnt[tid][2]};
+    for (int t = lo; t < hi; t++) order[p[weight(t)]++] = t;
+}
+
 constexpr int LDP = TS + 8;                 // one sample of one component plane, padded (bank-conflict free)
 constexpr int PLANE = KS * LDP + 8;         // component plane
 
@@ -313,13 +343,13 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 template <int NC, int MODE>
 __global__ void __launch_bounds__(256, 1)
 syrk_dmma2_kernel(const double* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, int ntile, int nsplit,
-                  const unsigned* __restrict__ tflags, double* __restrict__ Wk) {
+                  const unsigned* __restrict__ tflags, const int* __restrict__ order, double* __restrict__ Wk) {
     constexpr int PER = TS * NC * KS / 256;             // elements per thread per tile per chunk
     constexpr int TILE = NC * PLQ;                      // doubles per staged tile
     constexpr int STG = 2 * TILE;                       // A tile | B tile
     constexpr int SPI = 256 / (TS * NC);                // samples covered by one pass of the 256 threads (1 or 2)
     extern __shared__ __align__(16) double smem[];
-    int t = blockIdx.x;
+    int t = order ? order[blockIdx.x] : (int)blockIdx.x;   // heavy (two-component) tiles first, empty ones last
     int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
     while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
     while (ti * (ti + 1) / 2 > t) ti--;
@@ -529,25 +559,28 @@ __global__ void syrk_finalize_kernel(const double* __restrict__ Wre, const doubl
 template <typename T, int NC>
 int launch_syrk(nq_ctx_t ctx, const void* X, int64_t ldr, int64_t P, int64_t Ns, int ntile, int nsplit, int mode, double* W) {
     size_t smem = (size_t)4 * NC * PLANE * sizeof(double);
-    unsigned* flags = (unsigned*)nq_scratch(ctx, SL_W3, (size_t)ntile * sizeof(unsigned) + 16);
+    const int ntri = ntile * (ntile + 1) / 2;
+    unsigned* flags = (unsigned*)nq_scratch(ctx, SL_W3, ((size_t)ntile + ntri) * sizeof(unsigned) + 32);
     if (!flags) return NQ_ERR_ALLOC;
+    int* order = NC == 2 ? (int*)(flags + ntile) : nullptr;
     if (NC == 2 && mode == 0) {       // mode 1 (same launch sequence) reuses the flags
         NQ_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)ntile * sizeof(unsigned), ctx->stream));
         dim3 g((unsigned)((P * NC + 255) / 256), (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, Ns / 64)));
         NQ_LAUNCH(ctx, (tile_activity_kernel<T, NC>), g, 256, 0, (const T*)X, ldr, P, Ns, flags);
     }
-    dim3 grid((unsigned)(ntile * (ntile + 1) / 2), (unsigned)nsplit);
+    if (NC == 2) NQ_LAUNCH(ctx, tile_order_kernel, 1, 256, 0, (const unsigned*)flags, ntile, mode, order);
+    dim3 grid((unsigned)ntri, (unsigned)nsplit);
     static const bool old_path = [] { const char* e = getenv("NQ_SYRK_PATH"); return e && !strcmp(e, "staged"); }();
     if (sizeof(T) == 8 && !old_path) {
         size_t smem2 = (size_t)NSTAGE * 2 * NC * PLQ * sizeof(double);
         if (mode == 0) {
             auto kern2 = syrk_dmma2_kernel<NC, 0>;
             NQ_CUDA(ctx, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            NQ_LAUNCH(ctx, kern2, grid, 256, smem2, (const double*)X, ldr, P, Ns, ntile, nsplit, (const unsigned*)flags, W);
+            NQ_LAUNCH(ctx, kern2, grid, 256, smem2, (const double*)X, ldr, P, Ns, ntile, nsplit, (const unsigned*)flags, (const int*)order, W);
         } else {
             auto kern2 = syrk_dmma2_kernel<NC, 1>;
             NQ_CUDA(ctx, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            NQ_LAUNCH(ctx, kern2, grid, 256, smem2, (const double*)X, ldr, P, Ns, ntile, nsplit, (const unsigned*)flags, W);
+            NQ_LAUNCH(ctx, kern2, grid, 256, smem2, (const double*)X, ldr, P, Ns, ntile, nsplit, (const unsigned*)flags, (const int*)order, W);
         }
         return NQ_OK;
     }
