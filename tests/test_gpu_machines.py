@@ -25,6 +25,13 @@ CASES = [
     ("ndm", "spin", 7, 1, np.float64, OM.LOGCOSH, 13),
     ("ndm", "fock", 16, 2, np.float32, OM.SOFTPLUS, 50),
     ("ndm", "spin", 66, 4, np.float64, OM.SOFTPLUS, 6),       # multi-word, M = 264 > 256
+    # corners of the cfg5 throughput sweep (N = 64 ... 256, alpha = 1 ... 8)
+    ("rbm", "spin", 256, 1, np.complex128, OM.LOGCOSH, 9),    # four packed words
+    ("rbm", "spin", 128, 8, np.complex64, OM.LOGCOSH, 5),     # M = 1024
+    ("rbm", "spin", 64, 8, np.float64, OM.SOFTPLUS, 7),
+    ("ndm", "fock", 128, 2, np.float64, OM.SOFTPLUS, 4),      # P = 131 968
+    ("ndm", "fock", 256, 1, np.float32, OM.SOFTPLUS, 3),
+    ("rbmsplit", "fock", 200, 2, np.complex128, OM.SOFTPLUS, 3),
 ]
 
 
