@@ -103,13 +103,32 @@ def run_reference(args):
             "config": {"workload": WORKLOAD_NAME, "sample": sample},
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
 NCU_FUSED_DRAM_BYTES = 4.5096e9   # local_ndm3s_kernel<double>, cfg4, 65536 configurations per launch
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write banners to fd 1 (NCCL prints its version there on
+    rank 0), so fd 1 is pointed at stderr for the whole run and the line goes to a private copy of the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 FP64_TENSOR_PEAK = 37.2   # TFLOP/s, mma.sync m8n8k4 f64 at 8 warps/SM on this pool's B200 (profiles/fp64_peaks.json)
 
 
@@ -354,12 +373,13 @@ def run_gpu(args):
         line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
                                 "sample": "%d configurations of the same workload on %d OpenMP threads; C restatement of "
                                           "the reference algorithm (oracle/cref.c; Julia unavailable)" % (used, threads)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
