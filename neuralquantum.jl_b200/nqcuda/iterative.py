@@ -137,6 +137,32 @@ class BatchedSampler:
             return stat_analysis(ctx, (self.abs2.data_ptr(), self.B, self.L, net.rdtype))
         return stat_analysis(ctx, (self.loc.data_ptr(), self.B, self.L, net.cdtype))
 
+    # ---- observables on the stored samples (BatchedObsKetSampler.jl:32-59) ----
+    def add_observable_(self, name, obs):
+        """add_observable!(is, name, obs): `obs` is a LocalOperator on the physical Hilbert space."""
+        if self.is_liouvillian:
+            raise NotImplementedError("density-matrix observables need the diagonal sampler (BatchedObsDMSampler.jl), "
+                                      "which is outside the built path")
+        if not hasattr(self, "observables"):
+            self.observables, self._obs_dev, self._obs_loc = {}, {}, None
+        self.observables[name] = obs
+        self._obs_dev[name] = obs.to_device(self.ctx)
+
+    def compute_observables(self):
+        """compute_observables(is): O_loc of every stored configuration (same kernel as E_loc, chain reuse) and its
+        chain statistics, one Measurement per observable."""
+        torch = _torch()
+        res = {}
+        if not getattr(self, "observables", None):
+            return res
+        if self._obs_loc is None:
+            self._obs_loc = torch.zeros(self.Ns, dtype=self.loc.dtype, device=self.loc.device)
+        for name, dev in self._obs_dev.items():
+            L.check(L.lib.nq_local_scalar_packed(self.net.h, dev.h, self.prow.data_ptr(), None, self.Ns,
+                                                 self._obs_loc.data_ptr()), self.ctx.h)
+            res[name] = stat_analysis(self.ctx, (self._obs_loc.data_ptr(), self.B, self.L, self.net.cdtype))
+        return res
+
     def sample_(self, sample=True):
         """sample!(is) -> (Measurement of the cost, self as the preconditioner cache)."""
         if sample:

@@ -111,3 +111,37 @@ def test_steady_state_optimisation_reduces_cost(nq, ctx):
         bs.update_(nq.Descent(0.02))
         costs.append(stat.mean.real)
     assert np.mean(costs[-5:]) < 0.5 * np.mean(costs[:5])
+
+
+def test_ket_observables_on_stored_samples(nq, ctx):
+    """compute_observables (BatchedObsKetSampler.jl:32-59): O_loc of the stored samples through the E_loc kernel +
+    chain statistics, against the oracle's local estimator and stat_analysis."""
+    from oracle import estimators as OE
+    from oracle import stats as OST
+    from oracle import operators as OO
+    N, B, Lc = 8, 16, 20
+    oh, oH = tfim_1d(N)
+    ph, pH = H.p_tfim_1d(nq, N)
+    om, pm, hilb = H.make_pair(nq, ctx, "rbm", "spin", N, 2, np.complex128, OM.LOGCOSH)
+    bs = nq.BatchedSampler(pm, nq.MetropolisSampler(nq.LocalRule(), Lc, N, burn=10, seed=3), pH,
+                           nq.SR(np.float32, eps=0.1, algorithm="sr_cholesky"), batch_sz=B)
+    S = H.rand_states("spin", N, B * Lc, 77)
+    bs.set_samples(S.reshape(N, B, Lc, order="F"))
+    bs.evaluate()
+    # magnetisation along x and a two-site correlator, built with the same operator algebra on both sides
+    p_mx, o_mx = nq.LocalOperator(ph), None
+    for i in range(1, N + 1):
+        p_mx = p_mx + (1.0 / N) * nq.sigmax(ph, i)
+        o_mx = OO.add(o_mx, OO.scale(1.0 / N, OO.sigmax(oh, i)))
+    p_zz = nq.LocalOperator(ph) + nq.sigmaz(ph, 1) * nq.sigmaz(ph, 4)
+    o_zz = OO.mul(OO.sigmaz(oh, 1), OO.sigmaz(oh, 4))
+    bs.add_observable_("mx", p_mx)
+    bs.add_observable_("zz14", p_zz)
+    res = bs.compute_observables()
+    assert set(res) == {"mx", "zz14"}
+    for name, oop in (("mx", o_mx), ("zz14", o_zz)):
+        ref_loc = OE.local_scalar_ket(om, oop, S)
+        ref = OST.stat_analysis(ref_loc.reshape(B, Lc, order="F"))
+        m = res[name]
+        assert abs(m.mean - ref["mean"]) <= 1e-11 * max(1.0, abs(ref["mean"])), name
+        assert abs(m.error - ref["error"]) <= 1e-9 * max(1e-3, ref["error"]), name
