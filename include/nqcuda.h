@@ -188,6 +188,12 @@ int nq_sampler_set_state(nq_sampler_t s, const void* srow, const void* scol, nq_
 int nq_sampler_get_state(nq_sampler_t s, void* srow, void* scol, nq_dtype sdtype);
 /* rand!(rng, sigma, hilb): uniformly random configurations (Metropolis.jl:106) */
 int nq_sampler_randomize(nq_sampler_t s);
+/* Density-matrix machines (NDM): diagonal != 0 turns the chain into one over the diagonal rho(sigma, sigma) --
+ * sigma' follows sigma, proposals are drawn in 1..N and flip the site on both sides, p(sigma) ~ rho(sigma, sigma).
+ * This is the chain of the observables sampler (ref: IterativeInterface/Samplers/Obs/BatchedObsDMSampler.jl:59-105,
+ * base_batched_networks.jl:244-253).  The reference takes abs.(log rho) as the log-probability there (SURVEY quirk
+ * Q4); the library uses Re log rho(sigma, sigma), which is what the estimator needs.  Default 0 (joint chain). */
+int nq_sampler_set_mode(nq_sampler_t s, int diagonal);
 /* one samplenext! with supplied randomness: sites [passes,B] int32 1-based in 1..N (1..2N doubled),
  * uniforms [passes,B] of the machine's real type; accept_out [passes,B] uint8 (1 = accepted), may be NULL */
 int nq_sampler_replay(nq_sampler_t s, const int32_t* sites, const void* uniforms, uint8_t* accept_out);

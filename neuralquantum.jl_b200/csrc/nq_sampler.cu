@@ -21,6 +21,7 @@ struct nq_sampler_s {
     uint64_t seed;
     int64_t chain_offset;
     uint64_t pass_base;       // proposals already drawn per chain (Philox counter)
+    int diag;                 // 1: chain over the diagonal rho(sigma, sigma) (nq_sampler_set_mode)
     uint64_t* prow;           // device [B][W64]
     uint64_t* pcol;
     unsigned long long* accepted;   // device counter
@@ -75,7 +76,7 @@ __global__ void randomize_kernel(uint64_t* __restrict__ prow, uint64_t* __restri
 // shared memory per warp: items * (theta, f, theta_tentative, f_tentative)
 struct RunArgs {
     int64_t B;
-    int N, M, A, hilb, passes, burn, L, replay;
+    int N, M, A, hilb, passes, burn, L, replay, diag;
     uint64_t seed, pass_base;
     int64_t chain_offset;
     const int32_t* sites;      // replay: [passes][B], 1-based
@@ -283,10 +284,11 @@ __global__ void sampler_ndm_kernel(const T* __restrict__ par, const T* __restric
 #pragma unroll 1
         for (int ps = 0; ps < a.passes; ps++) {
             int pic = step * a.passes + ps;
-            if ((ps & 31) == 0) db.fill(a, chain, pic, a.passes - ps, 2 * N, lane);
+            if ((ps & 31) == 0) db.fill(a, chain, pic, a.passes - ps, a.diag ? N : 2 * N, lane);
             int site; T u;
             db.get(ps & 31, site, u);
-            const bool col = site >= N;
+            // diagonal mode: sigma' = sigma, a proposal flips site j of both (p ~ rho(sigma, sigma), which is real)
+            const bool col = !a.diag && site >= N;
             const int j = col ? site - N : site;
             const T dv = flip_delta<T>(a.hilb, get_bit(col ? cb : rb, j));
             const int sg = dv > T(0) ? 0 : 1;
@@ -308,18 +310,27 @@ __global__ void sampler_ndm_kernel(const T* __restrict__ par, const T* __restric
             for (int q = lane; q < A; q += 32) {
                 C Ep = cp[q], Em = ACT == NQ_LOGCOSH ? cm[q] : C(T(1), T(0));
                 if (col) { Ep.im = -Ep.im; Em.im = -Em.im; }
+                if (a.diag) {              // row and column factors multiply: E conj(E) = |E|^2, the ancilla stays real
+                    Ep = C(Ep.re * Ep.re + Ep.im * Ep.im, T(0));
+                    Em = C(Em.re * Em.re + Em.im * Em.im, T(0));
+                }
                 C fac, num;
                 ratio_parts<ACT>(spi[q], Ep, Em, fac, num);
-                pl *= abs2_d(fac);
+                pl *= a.diag ? (double)fac.re : abs2_d(fac);
                 tspi[q] = num; tspi[A + q] = fac;
             }
             pl = warp_prod(pl);
             const double pr = pl * (double)eb[sg * N + j];
             const bool acc = (u - (T)pr) < T(0);
             if (acc) {
-                for (int k = lane; k < M; k += 32) sl[so + k] = ratio_finish<ACT>(tsl[M + k], tsl[k]);
+                for (int k = lane; k < M; k += 32) {
+                    const T sn = ratio_finish<ACT>(tsl[M + k], tsl[k]);
+                    sl[so + k] = sn;
+                    if (a.diag) sl[M + k] = sn;
+                }
                 for (int q = lane; q < A; q += 32) spi[q] = ratio_finish<ACT>(tspi[A + q], tspi[q]);
-                if (col) cb[j >> 6] ^= 1ull << (j & 63); else rb[j >> 6] ^= 1ull << (j & 63);
+                if (col || a.diag) cb[j >> 6] ^= 1ull << (j & 63);
+                if (!col) rb[j >> 6] ^= 1ull << (j & 63);
                 nacc++;
             }
             __syncwarp();
@@ -402,6 +413,7 @@ RunArgs base_args(nq_sampler_t s) {
     nq_machine_t m = s->m;
     a.B = s->B; a.N = m->N; a.M = m->M; a.A = m->A; a.hilb = (int)m->hilb; a.passes = s->passes;
     a.seed = s->seed; a.pass_base = s->pass_base; a.chain_offset = s->chain_offset; a.accepted = s->accepted;
+    a.diag = s->diag;
     return a;
 }
 
@@ -417,7 +429,7 @@ extern "C" int nq_sampler_create(nq_machine_t m, int64_t B, int passes, uint64_t
     nq_sampler_t s = new nq_sampler_s();
     s->ctx = ctx; s->m = m; s->B = B;
     s->passes = (passes % 2 == 0) ? passes + 1 : passes;   // Metropolis.jl:30-38
-    s->seed = seed; s->chain_offset = chain_offset; s->pass_base = 0; s->passes_done = 0;
+    s->seed = seed; s->chain_offset = chain_offset; s->pass_base = 0; s->passes_done = 0; s->diag = 0;
     s->prow = s->pcol = nullptr; s->accepted = nullptr;
     size_t pbytes = (size_t)B * nq_words(m->N) * 8;
     bool ok = cudaMalloc((void**)&s->prow, pbytes) == cudaSuccess &&
@@ -449,6 +461,7 @@ extern "C" int nq_sampler_set_state(nq_sampler_t s, const void* srow, const void
     if (!s || !srow) return NQ_ERR_ARG;
     nq_machine_t m = s->m;
     nq_ctx_t ctx = m->ctx;
+    if (s->diag) scol = srow;             // diagonal chain: sigma' = sigma
     if (m->doubled() != (scol != nullptr)) return nq_fail(ctx, NQ_ERR_ARG, "row/col configuration mismatch");
     NQ_CUDA(ctx, cudaSetDevice(ctx->device));
     NqStage st(ctx);
@@ -487,6 +500,20 @@ extern "C" int nq_sampler_randomize(nq_sampler_t s) {
     int64_t n = s->B * W64;
     NQ_LAUNCH(ctx, randomize_kernel, (unsigned)((n + 255) / 256), 256, 0, s->prow, s->pcol, s->B, m->N, W64, s->seed,
               s->chain_offset, s->pass_base);
+    if (s->diag) NQ_CUDA(ctx, cudaMemcpyAsync(s->pcol, s->prow, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    return NQ_OK;
+}
+
+extern "C" int nq_sampler_set_mode(nq_sampler_t s, int diagonal) {
+    if (!s) return NQ_ERR_ARG;
+    nq_machine_t m = s->m;
+    nq_ctx_t ctx = m->ctx;
+    if (diagonal && m->kind != NQ_NDM)
+        return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "the diagonal chain needs a density matrix with a real positive diagonal (NDM)");
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    s->diag = diagonal ? 1 : 0;
+    if (s->diag)
+        NQ_CUDA(ctx, cudaMemcpyAsync(s->pcol, s->prow, (size_t)s->B * nq_words(m->N) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     return NQ_OK;
 }
 

@@ -11,7 +11,7 @@ from .machines import RBM, RBMSplit, NDM, af_softplus, af_logcosh, init_random_p
 from .samplers import MetropolisSampler, MetropolisSamplerCache, LocalRule
 from .algorithms import (SR, Descent, update_, local_scalar, local_grad, stat_analysis, Measurement, sr_cholesky,
                          sr_cg)
-from .iterative import BatchedSampler
+from .iterative import BatchedSampler, BatchedObsDMSampler
 from .parallel import shard_chains, init_comm, world_from_env
 
 

@@ -99,6 +99,7 @@ _PROTOS = {
     "nq_sampler_set_state": (_i32, [_vp, _vp, _vp, _i32]),
     "nq_sampler_get_state": (_i32, [_vp, _vp, _vp, _i32]),
     "nq_sampler_randomize": (_i32, [_vp]),
+    "nq_sampler_set_mode": (_i32, [_vp, _i32]),
     "nq_sampler_replay": (_i32, [_vp, _vp, _vp, _vp]),
     "nq_sampler_sample": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32]),
     "nq_sampler_counters": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),

@@ -198,3 +198,58 @@ class BatchedSampler:
         if dw.dtype != _tdtype(net.dtype):
             dw = dw.to(_tdtype(net.dtype))
         L.check(L.lib.nq_update(net.h, dw.data_ptr(), float(opt.eta)), self.ctx.h)
+
+
+class BatchedObsDMSampler:
+    """Observables of a density-matrix machine (BatchedObsDMSampler.jl:3-105): an independent Markov chain over the
+    diagonal, p(sigma) ~ rho(sigma, sigma), and per stored sigma the local estimator
+        O_loc(sigma) = sum_eta O(sigma, eta) rho(eta, sigma) / rho(sigma, sigma)
+    so that <O> = Tr(O rho) / Tr(rho) = mean O_loc.  Log-probability: Re log rho(sigma, sigma) (the reference writes
+    abs.(log rho), SURVEY quirk Q4 -- not reproduced)."""
+
+    def __init__(self, net, sampler, batch_sz=16, chain_length=None, chain_offset=0):
+        torch = _torch()
+        if not net.doubled or net.kind != L.NQ_NDM:
+            raise ValueError("BatchedObsDMSampler needs an NDM density matrix")
+        self.net, self.sampler, self.ctx = net, sampler, net.ctx
+        self.B = int(batch_sz)
+        self.cache = MetropolisSamplerCache(sampler, net, self.B, chain_offset=chain_offset)
+        self.cache.set_mode(True)
+        self.L = self.cache.loc_chain_length if chain_length is None else int(chain_length)
+        self.Ns = self.B * self.L
+        dev = torch.device("cuda", self.ctx.device)
+        W = L.lib.nq_states_words(net.N)
+        self.prow = torch.zeros((self.L, self.B, W), dtype=torch.int64, device=dev)
+        self.pcol = torch.zeros_like(self.prow)
+        self.loc = torch.zeros(self.Ns, dtype=_tdtype(net.cdtype), device=dev)
+        self.observables, self._dev, self.results = {}, {}, {}
+
+    def add_observable_(self, name, obs):
+        self.observables[name] = obs
+        self._dev[name] = obs.to_device_left(self.ctx)
+
+    def sample_states(self):
+        self.cache.randomize()
+        self.cache.sample(self.sampler.burn_length, self.L, packed_out=(self.prow.data_ptr(), self.pcol.data_ptr()))
+
+    def set_samples(self, sigma):
+        """Bypass the chain with supplied diagonal configurations [N, B, L] (parity tests)."""
+        a = np.asfortranarray(sigma).reshape(self.net.N, self.Ns, order="F")
+        for buf in (self.prow, self.pcol):
+            L.check(L.lib.nq_pack_states(self.ctx.h, self.net.hilb.code, self.net.N, self.Ns, L.ptr(a), L.nq_dtype(a.dtype),
+                                         buf.data_ptr()), self.ctx.h)
+
+    def local_values(self, name):
+        L.check(L.lib.nq_local_scalar_packed(self.net.h, self._dev[name].h, self.prow.data_ptr(), self.pcol.data_ptr(),
+                                             self.Ns, self.loc.data_ptr()), self.ctx.h)
+        return self.loc
+
+    def compute_observables(self, sample=True):
+        if not self.observables:
+            return None
+        if sample:
+            self.sample_states()
+        for name in self.observables:
+            self.local_values(name)
+            self.results[name] = stat_analysis(self.ctx, (self.loc.data_ptr(), self.B, self.L, self.net.cdtype))
+        return self.results

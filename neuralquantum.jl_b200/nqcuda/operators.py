@@ -167,6 +167,11 @@ class LocalOperator:
     def to_device(self, ctx):
         return DeviceOperator(ctx, self.tables(), self.hilb)
 
+    def to_device_left(self, ctx):
+        """The operator acting on the row index of a density matrix, O (x) 1: what the observable accumulator of a
+        density-matrix machine visits (connections change sigma, sigma' stays; BatchedObsDMSampler.jl:94-101)."""
+        return DeviceOperator(ctx, _flatten([(t, None) for t in self.terms], L.NQ_SUPER, self.hilb), self.hilb)
+
 
 def KLocalOperatorRow(hilb, sites, mat):
     return LocalOperator(hilb, [LocalTerm(hilb, sites, mat)])

@@ -56,6 +56,10 @@ class MetropolisSamplerCache:
         L.check(L.lib.nq_sampler_get_state(self.h, L.ptr(sr), L.ptr(sc), L.nq_dtype(dtype)), self.net.ctx.h)
         return (sr, sc) if self.net.doubled else sr
 
+    def set_mode(self, diagonal):
+        """diagonal=True: chain over rho(sigma, sigma) (density-matrix observables); False: joint (sigma, sigma')."""
+        L.check(L.lib.nq_sampler_set_mode(self.h, 1 if diagonal else 0), self.net.ctx.h)
+
     def randomize(self):
         L.check(L.lib.nq_sampler_randomize(self.h), self.net.ctx.h)
 

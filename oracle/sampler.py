@@ -59,3 +59,25 @@ def samplenext_replay(net, hilb, state, sites, uniforms, dtype=np.float64):
             cur = np.where(a[None, :], prop, cur)
         lp = np.where(a, lpp, lp)
     return cur, acc, margin
+
+
+def samplenext_diagonal_replay(net, hilb, state, sites, uniforms, dtype=np.float64):
+    """Diagonal chain of the density-matrix observables sampler (BatchedObsDMSampler.jl:59-105; diagonal evaluation
+    base_batched_networks.jl:244-246): sigma' = sigma, a proposal flips site j (1..N) of both, the log-probability is
+    Re log rho(sigma, sigma) -- the mathematically intended reading of base_batched_networks.jl:249-253, which writes
+    abs.(log rho) (not reproduced).  state [N, B]; sites, uniforms [passes, B]."""
+    cur = np.array(state, dtype=np.float64)
+    lp = np.real(net.logpsi(cur, cur))
+    passes, B = np.shape(sites)
+    acc = np.zeros((passes, B), dtype=bool)
+    margin = np.zeros((passes, B), dtype=np.float64)
+    for i in range(passes):
+        prop = propose(hilb, cur, sites[i])
+        lpp = np.real(net.logpsi(prop, prop))
+        ratio = np.exp(lpp - lp)
+        margin[i] = np.asarray(uniforms[i], np.float64) - ratio
+        a = (np.asarray(uniforms[i], dtype) - ratio.astype(dtype)) < 0
+        acc[i] = a
+        cur = np.where(a[None, :], prop, cur)
+        lp = np.where(a, lpp, lp)
+    return cur, acc, margin

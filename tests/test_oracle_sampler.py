@@ -58,6 +58,29 @@ def test_doubled_chain_samples_rho_squared():
     assert sst.chisquare(obs, p * obs.sum()).pvalue >= 0.01
 
 
+def test_diagonal_chain_samples_the_diagonal_of_rho():
+    """Density-matrix observables chain (BatchedObsDMSampler.jl): p(sigma) ~ rho(sigma, sigma), which is real positive
+    for the NDM; sigma' follows sigma."""
+    hilb = HomogeneousFock(3)
+    net = M.random_machine("ndm", 3, 2, seed=5, std=0.4)
+    rng = np.random.Generator(np.random.Philox(3))
+    B, passes = 64, 3
+    st = random_states(hilb, B, seed=1)
+    hist = np.zeros(8)
+    for it in range(170):
+        sites = rng.integers(1, hilb.n + 1, size=(passes, B))
+        u = rng.random((passes, B))
+        st, acc, margin = S.samplenext_diagonal_replay(net, hilb, st, sites, u)
+        if it >= 20 and it % 2 == 0:
+            for c in range(B):
+                hist[hilb.toint(st[:, c]) - 1] += 1
+    allS = hilb.all_states()
+    d = np.exp(net.logpsi(allS, allS))
+    assert np.max(np.abs(d.imag)) <= 1e-12 * np.abs(d).max() and np.all(d.real > 0)
+    p = d.real / d.real.sum()
+    assert sst.chisquare(hist, p * hist.sum()).pvalue >= 0.01
+
+
 def test_replay_decision_rule_and_site_mapping():
     hilb = HomogeneousFock(3)
     net = M.random_machine("rbmsplit", 3, 1, seed=4, std=0.5)
