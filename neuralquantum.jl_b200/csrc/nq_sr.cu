@@ -570,8 +570,7 @@ int launch_syrk(nq_ctx_t ctx, const void* X, int64_t ldr, int64_t P, int64_t Ns,
     }
     if (NC == 2) NQ_LAUNCH(ctx, tile_order_kernel, 1, 256, 0, (const unsigned*)flags, ntile, mode, order);
     dim3 grid((unsigned)ntri, (unsigned)nsplit);
-    static const bool old_path = [] { const char* e = getenv("NQ_SYRK_PATH"); return e && !strcmp(e, "staged"); }();
-    if (sizeof(T) == 8 && !old_path) {
+    if (sizeof(T) == 8) {
         size_t smem2 = (size_t)NSTAGE * 2 * NC * PLQ * sizeof(double);
         if (mode == 0) {
             auto kern2 = syrk_dmma2_kernel<NC, 0>;
@@ -670,54 +669,6 @@ __global__ void chol_panel_kernel(E* __restrict__ A, int64_t P, int64_t j0, int 
     }
 #pragma unroll
     for (int c = 0; c < NB; c++) if (c < nb) A[row + P * (j0 + c)] = x[c];
-}
-
-// trailing update C[i,l] -= sum_c X[i,c] conj(X[l,c]) on the lower tile triangle, 64x64 tiles, 4x4 per thread
-constexpr int KU = 16;
-template <typename E>
-__global__ void chol_update_kernel(E* __restrict__ A, int64_t P, int64_t j0, int nb) {
-    __shared__ E Xi[KU][64 + 1];
-    __shared__ E Xl[KU][64 + 1];
-    int t = blockIdx.x;
-    int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
-    while (ti * (ti + 1) / 2 > t) ti--;
-    int tj = t - ti * (ti + 1) / 2;
-    const int64_t base = j0 + nb;
-    const int64_t i0 = base + (int64_t)ti * 64, l0 = base + (int64_t)tj * 64;
-    const int tid = threadIdx.x;
-    const int tr = tid % 16, tc = tid / 16;   // 16x16 threads, 4x4 each
-    E acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = make_zero<E>();
-    for (int kh = 0; kh < nb; kh += KU) {
-        for (int e = tid; e < KU * 64; e += blockDim.x) {
-            int r = e % 64, c = e / 64;
-            Xi[c][r] = (kh + c < nb && i0 + r < P) ? A[(i0 + r) + P * (j0 + kh + c)] : make_zero<E>();
-            Xl[c][r] = (kh + c < nb && l0 + r < P) ? A[(l0 + r) + P * (j0 + kh + c)] : make_zero<E>();
-        }
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < KU; c++) {
-            E xi[4], xl[4];
-#pragma unroll
-            for (int a = 0; a < 4; a++) { xi[a] = Xi[c][tr + 16 * a]; xl[a] = Xl[c][tc + 16 * a]; }
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int b = 0; b < 4; b++) acc[a][b] += mulc(xi[a], xl[b]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            int64_t i = i0 + tr + 16 * a, l = l0 + tc + 16 * b;
-            if (i < P && l < P && i >= l) A[i + P * l] -= acc[a][b];
-        }
 }
 
 template <typename E> __device__ __forceinline__ E mk(double re, double im);
@@ -946,15 +897,10 @@ int cholesky_solve(nq_ctx_t ctx, E* A, int64_t P, E* x, int* dinfo) {
         NQ_LAUNCH(ctx, chol_panel_kernel<E>, gp, 128, 0, A, P, j0, nb, dinfo);
         if (below > 0) {
             int64_t nt = (below + 63) / 64;
-            static const bool scalar_update = [] { const char* e = getenv("NQ_CHOL_UPDATE"); return e && !strcmp(e, "scalar"); }();
-            if (scalar_update) {
-                NQ_LAUNCH(ctx, chol_update_kernel<E>, (unsigned)(nt * (nt + 1) / 2), 256, 0, A, P, j0, nb);
-            } else {
-                const size_t usmem = (size_t)2 * (sizeof(E) / 8) * NB * LDU * sizeof(double);
-                auto ku = chol_update_dmma_kernel<E>;
-                if (j0 == 0) NQ_CUDA(ctx, cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
-                NQ_LAUNCH(ctx, ku, (unsigned)(nt * (nt + 1) / 2), 256, usmem, A, P, j0, nb);
-            }
+            const size_t usmem = (size_t)2 * (sizeof(E) / 8) * NB * LDU * sizeof(double);
+            auto ku = chol_update_dmma_kernel<E>;
+            if (j0 == 0) NQ_CUDA(ctx, cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
+            NQ_LAUNCH(ctx, ku, (unsigned)(nt * (nt + 1) / 2), 256, usmem, A, P, j0, nb);
         }
     }
     static const bool single_cta = [] { const char* e = getenv("NQ_CHOL_TRSV"); return e && !strcmp(e, "single"); }();
