@@ -463,6 +463,74 @@ syrk_dmma2_kernel(const double* __restrict__ Xr, int64_t ldr, int64_t P, int64_t
             stage = stage == NSTAGE - 1 ? 0 : stage + 1;
         }
         cp_async_wait<0>();
+    } else if (NC == 2 && act == 3u) {
+        // both component pairs active (complex rows x complex rows): (re, im) stay interleaved in shared memory --
+        // 16-byte cp.async copies, 16-byte fragment loads that serve both components (row pitch LDI = 260 doubles:
+        // a quarter-warp covers all 32 banks), half the copy and load instructions of the planar path
+        constexpr int LDI = 2 * TS + 4;
+        constexpr int TILEI = KS * LDI;              // doubles per staged tile (<= TILE)
+        static_assert(TILEI <= 2 * PLQ, "interleaved tile must fit the planar stage");
+        for (int i = tid; i < NSTAGE * STG; i += 256) smem[i] = 0.0;
+        __syncthreads();
+        const int64_t nch = c_end - c_begin;
+        const int m = tid & (TS - 1), sh = tid >> 7;                      // row of the tile, sample parity
+        const bool okA = rowA + 2 * m < PR, okB = !diag && rowB + 2 * m < PR;
+        const double* sA = Xr + rowA + 2 * m + ldr * (c_begin * KS + sh);
+        const double* sB = Xr + rowB + 2 * m + ldr * (c_begin * KS + sh);
+        auto issue2 = [&](int64_t ch, int stage) {
+            double* As = smem + stage * STG + sh * LDI + 2 * m;
+            double* Bs = As + TILE;
+            const int64_t smp0 = (c_begin + ch) * KS + sh;
+            const double* pa = sA + ch * KS * ldr;
+            const double* pb = sB + ch * KS * ldr;
+#pragma unroll
+            for (int i = 0; i < KS / 2; i++) {
+                const bool ok = smp0 + 2 * i < Ns;
+                const int sz = ok ? 16 : 0;
+                if (okA) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"((unsigned)__cvta_generic_to_shared(As + 2 * i * LDI)), "l"(ok ? pa : Xr), "r"(sz) : "memory");
+                if (okB) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"((unsigned)__cvta_generic_to_shared(Bs + 2 * i * LDI)), "l"(ok ? pb : Xr), "r"(sz) : "memory");
+                pa += 2 * ldr; pb += 2 * ldr;
+            }
+        };
+#pragma unroll
+        for (int p = 0; p < NSTAGE - 1; p++) {
+            if (p < nch) issue2(p, p);
+            cp_async_commit();
+        }
+        int stage = 0;
+        for (int64_t it = 0; it < nch; it++) {
+            cp_async_wait<NSTAGE - 2>();
+            __syncthreads();
+            const int nstage = stage == 0 ? NSTAGE - 1 : stage - 1;
+            if (it + NSTAGE - 1 < nch) issue2(it + NSTAGE - 1, nstage);
+            cp_async_commit();
+            const double* A = smem + stage * STG;
+            const double2* Ap = reinterpret_cast<const double2*>(A) + wm * 64 + g;
+            const double2* Bp = reinterpret_cast<const double2*>(diag ? A : A + TILE) + wn * 32 + g;
+#pragma unroll
+            for (int k4 = 0; k4 < KS / 4; k4++) {
+                const int sidx = (4 * k4 + tq) * (LDI / 2);
+                double2 a[8], b[4];
+#pragma unroll
+                for (int i = 0; i < 8; i++) a[i] = Ap[sidx + i * 8];
+#pragma unroll
+                for (int j = 0; j < 4; j++) b[j] = Bp[sidx + j * 8];
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (MODE == 0) {
+                            dmma(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+                            dmma(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
+                        } else {
+                            dmma(acc[i][j][0], acc[i][j][1], a[i].x, b[j].y);
+                            dmma(acc[i][j][0], acc[i][j][1], a[i].y, -b[j].x);
+                        }
+                    }
+            }
+            stage = stage == NSTAGE - 1 ? 0 : stage + 1;
+        }
+        cp_async_wait<0>();
     } else if (act) {
         for (int i = tid; i < NSTAGE * STG; i += 256) smem[i] = 0.0;
         __syncthreads();
@@ -481,24 +549,6 @@ syrk_dmma2_kernel(const double* __restrict__ Xr, int64_t ldr, int64_t P, int64_t
             cp_async_commit();
             const double* A = smem + stage * STG;
             const double* Bm = diag ? A : A + TILE;
-            if (NC == 2 && MODE == 0 && act == 3u) {
-                // both components, same pairing on A and B: the two planes are just 16 rows of one K loop
-                const double* Ap = A + wm * 64 + g;
-                const double* Bp = Bm + wn * 32 + g;
-#pragma unroll
-                for (int k4 = 0; k4 < 2 * KS / 4; k4++) {
-                    const int sidx = (4 * k4 + tq) * LDQ;
-                    double a[8], b[4];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) a[i] = Ap[sidx + i * 8];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) b[j] = Bp[sidx + j * 8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                }
-            } else
 #pragma unroll
             for (int comp = 0; comp < NC; comp++) {
                 if (!((act >> comp) & 1u)) continue;
