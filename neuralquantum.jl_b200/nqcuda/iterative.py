@@ -141,8 +141,12 @@ class BatchedSampler:
     def add_observable_(self, name, obs):
         """add_observable!(is, name, obs): `obs` is a LocalOperator on the physical Hilbert space."""
         if self.is_liouvillian:
-            raise NotImplementedError("density-matrix observables need the diagonal sampler (BatchedObsDMSampler.jl), "
-                                      "which is outside the built path")
+            # the gradient sampler of a Liouvillian owns a diagonal-chain observables sampler (BatchedGradSampler.jl)
+            if getattr(self, "_obs_dm", None) is None:
+                self._obs_dm = BatchedObsDMSampler(self.net, self.sampler, batch_sz=self.B, chain_length=self.L,
+                                                   chain_offset=self.rank * self.B)
+            self._obs_dm.add_observable_(name, obs)
+            return
         if not hasattr(self, "observables"):
             self.observables, self._obs_dev, self._obs_loc = {}, {}, None
         self.observables[name] = obs
@@ -152,6 +156,9 @@ class BatchedSampler:
         """compute_observables(is): O_loc of every stored configuration (same kernel as E_loc, chain reuse) and its
         chain statistics, one Measurement per observable."""
         torch = _torch()
+        if self.is_liouvillian:
+            dm = getattr(self, "_obs_dm", None)
+            return dm.compute_observables() if dm is not None else {}
         res = {}
         if not getattr(self, "observables", None):
             return res
