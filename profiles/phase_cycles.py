@@ -30,7 +30,7 @@ lib = nq._lib.lib
 lib.nq_debug_phase_cycles(out, 1)
 bs.evaluate()
 lib.nq_debug_phase_cycles(out, 0)
-names = ["decode+conn list / operator pass", "base(+zero)", "phase AB / site phase", "phase C", "totals+A", "output"]
+names = ["decode + operator pass", "base quantities", "S1 ratio steps (v3: phase AB)", "W weights (v3: phase C)", "(v3: totals)", "S2 + output"]
 tot = sum(out[:6])
 for n, v in zip(names, out):
     print("%-38s %6.1f%%  %8.0f cycles/sample" % (n, 100.0 * v / tot, v / (w["chains"] * w["L"])))
