@@ -109,7 +109,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-NCU_FUSED_DRAM_BYTES = 4.5096e9   # local_ndm3s_kernel<double>, cfg4, 65536 configurations per launch
+NCU_FUSED_DRAM_BYTES = 4.5096e9   # local_ndm3t_kernel<double>, cfg4, 65536 configurations per launch
 _REAL_STDOUT = None
 
 
@@ -340,7 +340,7 @@ def run_gpu(args):
     bytes_eval = Ns * (P * es + es + 2 * 8)               # O row + log rho + two packed words per configuration
     bytes_fused = Ns * (2 * P * es + 2 * es + 2 * 8)      # O row + grad L_loc row + log rho + L_loc + packed words
     ach = bytes_fused / (t_loc * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "local_ndm3s_kernel<double,softplus,grad,with_O> (fused eval+grad+estimator)",
+    roof = {"bound": "hbm", "kernel": "local_ndm3t_kernel<double,softplus,grad,with_O> (fused eval+grad+estimator)",
             "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r1k_top_kernels.txt)
             "traffic": NCU_FUSED_DRAM_BYTES if (world == 1 and Ns == 65536) else None,
@@ -349,7 +349,7 @@ def run_gpu(args):
             "all": {"ndm_evalgrad_kernel (stand-alone nq_logpsi_grad)": {
                         "ms": t_eval, "GB/s": bytes_eval / (t_eval * 1e-3) / 1e9,
                         "frac": bytes_eval / (t_eval * 1e-3) / 1e9 / pk["hbm_gbs"]},
-                    "local_ndm3s_kernel (fused)": {"ms": t_loc, "GB/s": ach, "frac": ach / pk["hbm_gbs"]},
+                    "local_ndm3t_kernel (fused)": {"ms": t_loc, "GB/s": ach, "frac": ach / pk["hbm_gbs"]},
                     "syrk_dmma2_kernel (S assembly, nq_sr_setup)": {
                         "bound": "tensor", "ms": t_setup, "achieved": flops_setup / (t_setup * 1e-3) / 1e12, "unit": "TFLOP/s",
                         "peak": FP64_TENSOR_PEAK, "frac": flops_setup / (t_setup * 1e-3) / 1e12 / FP64_TENSOR_PEAK,
