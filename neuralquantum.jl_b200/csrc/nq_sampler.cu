@@ -239,12 +239,13 @@ __global__ void sampler_ndm_kernel(const T* __restrict__ par, const T* __restric
     }
     __syncthreads();
     if (chain >= a.B) return;
-    const size_t per_warp = (size_t)(4 * M) * sizeof(T) + (size_t)(3 * A) * sizeof(C);
+    const size_t per_warp = (size_t)(4 * M + 2 * N) * sizeof(T) + (size_t)(3 * A) * sizeof(C);
     unsigned char* base = smem_raw + ((size_t)2 * N * sizeof(T) + 15) / 16 * 16 + (size_t)warp * ((per_warp + 15) / 16 * 16);
     C* spi = (C*)base;            // [A]
     C* tspi = spi + A;            // [2A]: numerators, then factors
     T* sl = (T*)(tspi + 2 * A);   // [2M]
     T* tsl = sl + 2 * M;          // [2M]: numerators, then factors
+    T* vsw = tsl + 2 * M;         // [2N]: site values of (sigma, sigma') for the refresh of theta
     const T half = T(0.5);
     uint64_t rb[MAXW], cb[MAXW];
 #pragma unroll
@@ -255,13 +256,15 @@ __global__ void sampler_ndm_kernel(const T* __restrict__ par, const T* __restric
     unsigned nacc = 0;
     const int nsteps = a.burn + a.L;
     for (int step = 0; step < nsteps; step++) {
+        for (int i = lane; i < 2 * N; i += 32) vsw[i] = digit_value<T>(a.hilb, get_bit(i < N ? rb : cb, i < N ? i : i - N));
+        __syncwarp();
         for (int k = lane; k < M; k += 32) {
             const T* __restrict__ w = par + o_wlam + k;
             T t = par[o_hlam + k], tp = t;
             for (int j = 0; j < N; j++) {
                 T wv = w[(int64_t)M * j];
-                t += wv * digit_value<T>(a.hilb, get_bit(rb, j));
-                tp += wv * digit_value<T>(a.hilb, get_bit(cb, j));
+                t += wv * vsw[j];
+                tp += wv * vsw[N + j];
             }
             T f, d, fp, dp;
             act_eval<ACT>(t, f, d);
@@ -271,7 +274,7 @@ __global__ void sampler_ndm_kernel(const T* __restrict__ par, const T* __restric
         for (int q = lane; q < A; q += 32) {
             T pr = par[o_dlam + q], pim = T(0);
             for (int j = 0; j < N; j++) {
-                T x = digit_value<T>(a.hilb, get_bit(rb, j)), y = digit_value<T>(a.hilb, get_bit(cb, j));
+                T x = vsw[j], y = vsw[N + j];
                 pr += half * par[o_ulam + q + (int64_t)A * j] * (x + y);
                 pim += half * par[o_umu + q + (int64_t)A * j] * (x - y);
             }
@@ -368,7 +371,7 @@ template <typename T, int ACT>
 int launch_sampler_ndm(nq_sampler_t s, const RunArgs& a) {
     nq_machine_t m = s->m;
     nq_ctx_t ctx = m->ctx;
-    size_t per_warp = ((size_t)4 * m->M * sizeof(T) + (size_t)3 * m->A * sizeof(cx<T>) + 15) / 16 * 16;
+    size_t per_warp = ((size_t)(4 * m->M + 2 * m->N) * sizeof(T) + (size_t)3 * m->A * sizeof(cx<T>) + 15) / 16 * 16;
     const size_t tab_bytes = ((size_t)2 * m->N * sizeof(T) + 15) / 16 * 16;
     const cx<T>* tabc = (const cx<T>*)((const char*)m->etab + ((size_t)4 * m->M * m->N * sizeof(T) + 15) / 16 * 16);
     int wpb = 8;
