@@ -99,6 +99,46 @@ def test_local_liouvillian_value_and_gradient(nq, ctx, kind, dtype, act, N, alph
     H.assert_close(nq.local_scalar(pm, dop, (R, Cc)), OE.local_scalar_super(om, ol, R, Cc), tol, "L_loc (scalar)")
 
 
+@pytest.mark.parametrize("N,alpha,alpha_a,act,hk", [
+    (44, 0.5, 0.5, OM.SOFTPLUS, "fock"),      # 3 N = 132 (site, pattern) weights > 128 threads per configuration
+    (12, 3, 1, OM.SOFTPLUS, "fock"),          # M = 36 > 32 hidden units per layer (two passes per lane), A = 12 != M
+    (10, 1, 4, OM.LOGCOSH, "spin"),           # A = 40 > M = 10
+])
+def test_local_liouvillian_odd_shapes(nq, ctx, N, alpha, alpha_a, act, hk):
+    """Shapes that leave the one-hidden-unit-per-lane / one-thread-per-weight sweet spot of the fused NDM kernel."""
+    _, _, _, ol = lindblad_ising_1d(N, 0.4, 2.0, fock=(hk == "fock"))
+    _, _, _, pl = H.p_lindblad_ising_1d(nq, N, 0.4, 2.0, fock=(hk == "fock"))
+    om, pm, hilb = H.make_pair(nq, ctx, "ndm", hk, N, alpha, np.float64, act, alpha_a=alpha_a)
+    dop = pl.to_device(ctx)
+    B = 6
+    R, Cc = H.rand_states(hk, N, B, 41), H.rand_states(hk, N, B, 42)
+    Cc[:, :2] = R[:, :2]
+    ref_l, ref_g = OE.local_grad_super(om, ol, R, Cc)
+    loc, g = nq.local_grad(pm, dop, (R, Cc))
+    H.assert_close(loc, ref_l, 1e-11, "L_loc")
+    H.assert_close(g, ref_g, 1e-11, "grad L_loc")
+    ref_lp, ref_O = om.logpsi_grad(R, Cc)
+    # fused entry point (eval + grad + estimator in one launch) on the same configurations
+    L = nq._lib
+    import torch
+    W = L.lib.nq_states_words(N)
+    prow = torch.zeros((B, W), dtype=torch.int64, device="cuda")
+    pcol = torch.zeros_like(prow)
+    for arr, buf in ((R, prow), (Cc, pcol)):
+        a = np.asfortranarray(arr)
+        L.check(L.lib.nq_pack_states(ctx.h, hilb.code, N, B, L.ptr(a), L.nq_dtype(a.dtype), buf.data_ptr()), ctx.h)
+    lp = torch.zeros(B, dtype=torch.complex128, device="cuda")
+    O = torch.zeros((B, pm.P), dtype=torch.complex128, device="cuda")
+    lo = torch.zeros(B, dtype=torch.complex128, device="cuda")
+    gl = torch.zeros((B, pm.P), dtype=torch.complex128, device="cuda")
+    L.check(L.lib.nq_logpsi_grad_local_packed(pm.h, dop.h, prow.data_ptr(), pcol.data_ptr(), B, lp.data_ptr(), O.data_ptr(),
+                                              pm.P, lo.data_ptr(), gl.data_ptr(), pm.P), ctx.h)
+    H.assert_close(lp.cpu().numpy(), ref_lp, 1e-11, "log rho (fused)")
+    H.assert_close(O.cpu().numpy().T, ref_O, 1e-11, "O (fused)")
+    H.assert_close(lo.cpu().numpy(), ref_l, 1e-11, "L_loc (fused)")
+    H.assert_close(gl.cpu().numpy().T, ref_g, 1e-11, "grad L_loc (fused)")
+
+
 def test_estimator_argument_errors(nq, ctx):
     _, pH = H.p_tfim_1d(nq, 6)
     _, _, _, pl = H.p_lindblad_ising_1d(nq, 6)
