@@ -4,7 +4,8 @@
 //                                    (HBM-bound streaming passes, FP64 accumulation, fixed order)
 //   K7  nq_sr_setup                  S = Oc Oc^H / Ns as a split-K SYRK/HERK on the FP64 tensor path
 //                                    (mma.sync m8n8k4 f64 = DMMA; tcgen05 has no FP64 kind), lower
-//                                    tile triangle only, deterministic two-stage reduction
+//                                    tile triangle only, deterministic two-stage reduction; FP32-mode
+//                                    operands go to the tcgen05 3xTF32 kernel in nq_syrk_tf32.cu
 //   K8  nq_sr_solve(_matfree)        blocked Cholesky (cuSOLVER-free) or CG (IterativeSolvers 0.8.1 rule)
 //   K9  nq_update                    w <- w - eta dw
 //
@@ -721,12 +722,6 @@ __global__ void chol_panel_kernel(E* __restrict__ A, int64_t P, int64_t j0, int 
     for (int c = 0; c < NB; c++) if (c < nb) A[row + P * (j0 + c)] = x[c];
 }
 
-template <typename E> __device__ __forceinline__ E mk(double re, double im);
-template <> __device__ __forceinline__ double mk<double>(double re, double) { return re; }
-template <> __device__ __forceinline__ cxd mk<cxd>(double re, double im) { return cxd(re, im); }
-template <typename E> __device__ __forceinline__ E bcast(E v, int src) {
-    return mk<E>(__shfl_sync(0xffffffffu, real_part(v), src), __shfl_sync(0xffffffffu, imag_part(v), src));
-}
 
 // trailing update on the FP64 tensor pipe: A[i,l] -= sum_c X[i,c] conj(X[l,c]) for the lower 64x64 tiles, K = nb <= 32.
 // Panel rows staged as planar (re | im) [c][row] with pitch 68 (conflict-free fragment loads); 8 warps as
