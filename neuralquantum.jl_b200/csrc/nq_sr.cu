@@ -809,6 +809,10 @@ __global__ void __launch_bounds__(256) chol_update_dmma_kernel(E* __restrict__ A
             }
 }
 
+template <typename E> __device__ __forceinline__ E mk(double re, double im);
+template <> __device__ __forceinline__ double mk<double>(double re, double) { return re; }
+template <> __device__ __forceinline__ cxd mk<cxd>(double re, double im) { return cxd(re, im); }
+
 // forward L y = b (right-looking, coalesced row updates) then backward L^H x = y (left-looking,
 // coalesced column dot products); a single CTA walks the block columns.
 template <typename E>
