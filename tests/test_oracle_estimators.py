@@ -135,3 +135,23 @@ def test_iteration_drivers_run():
     a, b = full_super_states(hilb)
     r = sr.iteration_liouvillian(ndm, liouv, a, b, 1e-3)
     assert r["dw"].dtype == np.float64 and np.all(np.isfinite(r["dw"]))
+
+
+def test_density_matrix_observable_estimator_is_trace_formula():
+    """Observables of a density matrix (BatchedObsDMSampler.jl): with p(sigma) ~ rho(sigma, sigma) and the operator
+    acting on the row index, sum_sigma p(sigma) O_loc(sigma) = Tr(O rho) / Tr(rho) on the full space."""
+    from oracle.hilbert import HomogeneousFock
+    N = 3
+    hilb = HomogeneousFock(N)
+    net = M.random_machine("ndm", N, 2, seed=9, std=0.4)
+    allS = hilb.all_states()
+    D = allS.shape[1]
+    rho = np.exp(net.logpsi(np.repeat(allS, D, axis=1), np.tile(allS, (1, D)))).reshape(D, D)     # rho[row, col]
+    assert np.allclose(rho, rho.conj().T, atol=1e-12)                  # Hermitian by construction of the NDM
+    p = np.diag(rho).real
+    assert np.all(p > 0)
+    O = ops.add(ops.mul(ops.sigmay(hilb, 1), ops.sigmaz(hilb, 3)), ops.scale(0.5, ops.sigmax(hilb, 2)))
+    left = ops.KLocalLiouvillian(hilb, ops._tensor_left(O), None, None)
+    loc = E.local_scalar_super(net, left, allS, allS)
+    exact = np.trace(ops.to_matrix(O) @ rho) / np.trace(rho)
+    assert abs(np.sum(p * loc) / p.sum() - exact) <= 1e-12 * max(1.0, abs(exact))
