@@ -1136,6 +1136,84 @@ int cg_solve(CgOps<E>& ops, const E* b, double tol, int64_t maxiter, E* x, int64
     return residual <= reltol ? NQ_OK : NQ_ERR_NOT_CONVERGED;
 }
 
+// ---- MINRES (Paige & Saunders) on the same operator: Hermitian A = S + eps I (explicit or matrix-free), x0 = 0,
+// no preconditioner, stop when the recurrence residual ||r_k|| = phibar <= tol ||b||.  ref: the sr_minres branch of
+// SRIterative.jl:101-125 (IterativeSolvers 0.8.1 minres); the reference pins neither iterates nor iteration counts,
+// so parity is on the converged solution.
+template <typename E> __global__ void scale_copy_kernel(E* __restrict__ out, const E* __restrict__ in, double s, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rscale(s, in[i]);
+}
+template <typename E> __global__ void axpy_real_kernel(E* __restrict__ y, double a, const E* __restrict__ x, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = y[i] + rscale(a, x[i]);
+}
+// wn = (v - oldeps w1 - delta w2) / gamma written over w1;  x += phi wn
+template <typename E>
+__global__ void minres_w_kernel(E* __restrict__ w1, const E* __restrict__ w2, const E* __restrict__ v, E* __restrict__ x,
+                                double oldeps, double delta, double denom, double phi, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    E t = rscale(denom, v[i] - rscale(oldeps, w1[i]) - rscale(delta, w2[i]));
+    w1[i] = t;
+    x[i] = x[i] + rscale(phi, t);
+}
+
+template <typename E>
+int minres_solve(CgOps<E>& ops, const E* b, double tol, int64_t maxiter, E* x, int64_t* iters) {
+    nq_ctx_t ctx = ops.ctx;
+    const int64_t P = ops.P;
+    E* work = (E*)nq_scratch(ctx, SL_W2, (size_t)6 * P * sizeof(E) + 64);
+    double* dsc = (double*)nq_scratch(ctx, SL_W1, 64);
+    if (!work || !dsc) return NQ_ERR_ALLOC;
+    E *r1 = work, *r2 = work + P, *y = work + 2 * P, *v = work + 3 * P, *wa = work + 4 * P, *wb = work + 5 * P;
+    const unsigned gv = (unsigned)((P + 255) / 256);
+    NQ_CUDA(ctx, cudaMemsetAsync(x, 0, (size_t)P * sizeof(E), ctx->stream));
+    NQ_CUDA(ctx, cudaMemsetAsync(wa, 0, (size_t)2 * P * sizeof(E), ctx->stream));
+    NQ_CUDA(ctx, cudaMemcpyAsync(r2, b, (size_t)P * sizeof(E), cudaMemcpyDeviceToDevice, ctx->stream));
+    NQ_CUDA(ctx, cudaMemsetAsync(r1, 0, (size_t)P * sizeof(E), ctx->stream));
+    double h[2];
+    auto dot = [&](const E* a_, const E* b_, double* out) -> int {
+        NQ_LAUNCH(ctx, dot_kernel<E>, 1, 1024, 0, a_, b_, P, dsc);
+        NQ_CUDA(ctx, cudaMemcpyAsync(h, dsc, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *out = h[0];
+        return NQ_OK;
+    };
+    double bb;
+    NQ_CHECK(dot(r2, r2, &bb));
+    const double beta1 = sqrt(bb);
+    int64_t it = 0;
+    if (beta1 == 0.0) { if (iters) *iters = 0; return NQ_OK; }
+    double oldb = 0.0, beta = beta1, dbar = 0.0, epsln = 0.0, phibar = beta1, cs = -1.0, sn = 0.0;
+    while (it < maxiter && !(phibar <= tol * beta1)) {
+        it++;
+        NQ_LAUNCH(ctx, scale_copy_kernel<E>, gv, 256, 0, v, (const E*)r2, 1.0 / beta, P);          // v = r2 / beta
+        NQ_CHECK(ops.matvec(v, y));                                                                // y = A v
+        if (it >= 2) NQ_LAUNCH(ctx, axpy_real_kernel<E>, gv, 256, 0, y, -beta / oldb, (const E*)r1, P);
+        double alfa;
+        NQ_CHECK(dot(v, y, &alfa));                                                                // Re <v, y>
+        NQ_LAUNCH(ctx, axpy_real_kernel<E>, gv, 256, 0, y, -alfa / beta, (const E*)r2, P);
+        { E* t = r1; r1 = r2; r2 = y; y = t; }                                                     // r1 <- r2, r2 <- y
+        oldb = beta;
+        double b2;
+        NQ_CHECK(dot(r2, r2, &b2));
+        beta = sqrt(b2);
+        const double oldeps = epsln, delta = cs * dbar + sn * alfa, gbar = sn * dbar - cs * alfa;
+        epsln = sn * beta; dbar = -cs * beta;
+        double gamma = sqrt(gbar * gbar + beta * beta);
+        if (gamma < 1e-300) gamma = 1e-300;
+        cs = gbar / gamma; sn = beta / gamma;
+        const double phi = cs * phibar;
+        phibar = sn * phibar;
+        NQ_LAUNCH(ctx, minres_w_kernel<E>, gv, 256, 0, wa, (const E*)wb, (const E*)v, x, oldeps, delta, 1.0 / gamma, phi, P);
+        { E* t = wa; wa = wb; wb = t; }                                                            // (w_{k-1}, w_k)
+        if (beta == 0.0) break;                                                                    // exact solution reached
+    }
+    if (iters) *iters = it;
+    return (phibar <= tol * beta1 || beta == 0.0) ? NQ_OK : NQ_ERR_NOT_CONVERGED;
+}
+
 template <typename E>
 __global__ void update_kernel(E* __restrict__ w, const E* __restrict__ dw, typename elem_traits<E>::real eta, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -1415,17 +1493,20 @@ extern "C" int nq_sr_solve(nq_ctx_t ctx, void* S, const void* F, int64_t P, nq_d
             ctx->info = hinfo;
             status = nq_fail(ctx, NQ_ERR_NOT_POSDEF, "Cholesky: non-positive pivot at index %d", hinfo);
         }
-    } else if (algo == NQ_SOLVE_CG) {
+    } else if (algo == NQ_SOLVE_CG || algo == NQ_SOLVE_MINRES) {
         if (maxiter <= 0) maxiter = 10 * P;
+        const bool mr = algo == NQ_SOLVE_MINRES;
         if (cplx) {
             CgOps<cxd> ops; ops.ctx = ctx; ops.P = P; ops.S = (const cxd*)A; ops.eps = eps;
-            status = cg_solve<cxd>(ops, (const cxd*)b, tol, maxiter, (cxd*)x, &its);
+            status = mr ? minres_solve<cxd>(ops, (const cxd*)b, tol, maxiter, (cxd*)x, &its)
+                        : cg_solve<cxd>(ops, (const cxd*)b, tol, maxiter, (cxd*)x, &its);
         } else {
             CgOps<double> ops; ops.ctx = ctx; ops.P = P; ops.S = (const double*)A; ops.eps = eps;
-            status = cg_solve<double>(ops, (const double*)b, tol, maxiter, (double*)x, &its);
+            status = mr ? minres_solve<double>(ops, (const double*)b, tol, maxiter, (double*)x, &its)
+                        : cg_solve<double>(ops, (const double*)b, tol, maxiter, (double*)x, &its);
         }
         if (status != NQ_OK && status != NQ_ERR_NOT_CONVERGED) return status;
-        if (status == NQ_ERR_NOT_CONVERGED) nq_fail(ctx, status, "CG: not converged after %lld iterations", (long long)its);
+        if (status == NQ_ERR_NOT_CONVERGED) nq_fail(ctx, status, "%s: not converged after %lld iterations", algo == NQ_SOLVE_MINRES ? "MINRES" : "CG", (long long)its);
     } else return nq_fail(ctx, NQ_ERR_ARG, "unknown solver");
     if (iters) *iters = its;
     {
@@ -1437,10 +1518,12 @@ extern "C" int nq_sr_solve(nq_ctx_t ctx, void* S, const void* F, int64_t P, nq_d
     return fs != NQ_OK ? fs : status;
 }
 
-extern "C" int nq_sr_solve_matfree(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total,
-                                   nq_dtype dtype, const void* F, int real_params, double eps, double tol, int64_t maxiter,
-                                   void* dw, int64_t* iters) {
+static int sr_solve_matfree_impl(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total,
+                                 nq_dtype dtype, const void* F, int real_params, double eps, nq_solver algo, double tol,
+                                 int64_t maxiter, void* dw, int64_t* iters) {
     if (!ctx || !Oc || !F || !dw || P <= 0 || Ns <= 0 || ldO < P || Ns_total < Ns) return NQ_ERR_ARG;
+    if (algo != NQ_SOLVE_CG && algo != NQ_SOLVE_MINRES) return nq_fail(ctx, NQ_ERR_ARG, "matrix-free SR needs an iterative solver");
+    const bool mr = algo == NQ_SOLVE_MINRES;
     NQ_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!nq_is_device_ptr(Oc)) return nq_fail(ctx, NQ_ERR_ARG, "Oc must be device-resident");
     const bool out_complex = nq_dtype_is_complex(dtype) && !real_params;
@@ -1462,18 +1545,32 @@ extern "C" int nq_sr_solve_matfree(nq_ctx_t ctx, const void* Oc, int64_t ldO, in
     int64_t its = 0;
     if (out_complex) {
         CgOps<cxd> ops; ops.ctx = ctx; ops.P = P; ops.eps = eps; ops.O = Oc; ops.ld = ldO; ops.Ns = Ns; ops.Ns_total = Ns_total; ops.odtype = dtype;
-        status = cg_solve<cxd>(ops, (const cxd*)b, tol, maxiter, (cxd*)x, &its);
+        status = mr ? minres_solve<cxd>(ops, (const cxd*)b, tol, maxiter, (cxd*)x, &its)
+                    : cg_solve<cxd>(ops, (const cxd*)b, tol, maxiter, (cxd*)x, &its);
     } else {
         CgOps<double> ops; ops.ctx = ctx; ops.P = P; ops.eps = eps; ops.O = Oc; ops.ld = ldO; ops.Ns = Ns; ops.Ns_total = Ns_total; ops.odtype = dtype;
-        status = cg_solve<double>(ops, (const double*)b, tol, maxiter, (double*)x, &its);
+        status = mr ? minres_solve<double>(ops, (const double*)b, tol, maxiter, (double*)x, &its)
+                    : cg_solve<double>(ops, (const double*)b, tol, maxiter, (double*)x, &its);
     }
     if (status != NQ_OK && status != NQ_ERR_NOT_CONVERGED) return status;
-    if (status == NQ_ERR_NOT_CONVERGED) nq_fail(ctx, status, "CG: not converged after %lld iterations", (long long)its);
+    if (status == NQ_ERR_NOT_CONVERGED) nq_fail(ctx, status, "%s: not converged after %lld iterations", algo == NQ_SOLVE_MINRES ? "MINRES" : "CG", (long long)its);
     if (iters) *iters = its;
     NQ_LAUNCH(ctx, convert_to_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const void*)x, t, P, (int)wdt);
     NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)t, ddw, P, (int)sdt, 0);
     int fs = st.finish();
     return fs != NQ_OK ? fs : status;
+}
+
+extern "C" int nq_sr_solve_matfree(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total,
+                                   nq_dtype dtype, const void* F, int real_params, double eps, double tol, int64_t maxiter,
+                                   void* dw, int64_t* iters) {
+    return sr_solve_matfree_impl(ctx, Oc, ldO, P, Ns, Ns_total, dtype, F, real_params, eps, NQ_SOLVE_CG, tol, maxiter, dw, iters);
+}
+
+extern "C" int nq_sr_solve_matfree_algo(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total,
+                                        nq_dtype dtype, const void* F, int real_params, double eps, nq_solver algo, double tol,
+                                        int64_t maxiter, void* dw, int64_t* iters) {
+    return sr_solve_matfree_impl(ctx, Oc, ldO, P, Ns, Ns_total, dtype, F, real_params, eps, algo, tol, maxiter, dw, iters);
 }
 
 extern "C" int nq_update(nq_machine_t m, const void* dw, double eta) {

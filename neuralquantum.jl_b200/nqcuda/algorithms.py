@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib as L
 
-sr_cholesky, sr_cg = "sr_cholesky", "sr_cg"
+sr_cholesky, sr_cg, sr_minres = "sr_cholesky", "sr_cg", "sr_minres"
 sr_shift = "sr_shift"
 
 
@@ -67,8 +67,8 @@ class SR:
                  precondition_type=sr_shift):
         if precondition_type != sr_shift:
             raise NotImplementedError("only sr_shift is on the built path (SURVEY 8f)")
-        if algorithm not in (sr_cholesky, sr_cg):
-            raise NotImplementedError("sr_cholesky and sr_cg are on the built path (SURVEY 8f)")
+        if algorithm not in (sr_cholesky, sr_cg, sr_minres):
+            raise NotImplementedError("sr_cholesky, sr_cg and sr_minres are on the built path (SURVEY 8f)")
         self.sr_diag_shift = float(np.dtype(T).type(eps))
         self.sr_precision = float(np.dtype(T).type(precision))
         self.algorithm, self.full_matrix = algorithm, full_matrix

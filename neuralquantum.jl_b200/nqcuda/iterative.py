@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from .algorithms import Measurement, SR, sr_cg, sr_cholesky, stat_analysis
+from .algorithms import Measurement, SR, sr_cg, sr_cholesky, sr_minres, stat_analysis
 from .operators import Liouvillian
 from .samplers import MetropolisSamplerCache
 
@@ -184,14 +184,15 @@ class BatchedSampler:
         ctx, P, algo = self.ctx, self.net.P, self.algo
         its = C.c_int64()
         sd = L.nq_dtype(self.sdtype)
+        solver = {sr_cholesky: L.NQ_SOLVE_CHOLESKY, sr_cg: L.NQ_SOLVE_CG, sr_minres: L.NQ_SOLVE_MINRES}[algo.algorithm]
         if self.S is not None:
-            solver = L.NQ_SOLVE_CHOLESKY if algo.algorithm == sr_cholesky else L.NQ_SOLVE_CG
             st = L.lib.nq_sr_solve(ctx.h, self.S.data_ptr(), self.F.data_ptr(), P, sd, algo.sr_diag_shift, solver,
                                    algo.sr_precision, 0, self.dw.data_ptr(), C.byref(its))
         else:
-            st = L.lib.nq_sr_solve_matfree(ctx.h, self.O.data_ptr(), P, P, self.Ns, self.Ns_total,
-                                           L.nq_dtype(self.net.out_dtype), self.F.data_ptr(), int(self.real_params),
-                                           algo.sr_diag_shift, algo.sr_precision, 0, self.dw.data_ptr(), C.byref(its))
+            st = L.lib.nq_sr_solve_matfree_algo(ctx.h, self.O.data_ptr(), P, P, self.Ns, self.Ns_total,
+                                                L.nq_dtype(self.net.out_dtype), self.F.data_ptr(), int(self.real_params),
+                                                algo.sr_diag_shift, solver, algo.sr_precision, 0, self.dw.data_ptr(),
+                                                C.byref(its))
         self.last_iters = its.value
         if st == L.NQ_ERR_NOT_CONVERGED:       # reference: zero update after failed restarts
             self.dw.zero_()

@@ -144,3 +144,47 @@ def iteration_liouvillian(net, liouv, srow, scol, eps, real_params=None):
     dw = solve_cholesky(S, F, eps)
     return dict(logpsi=out, O=O, Lloc=Lloc, gLloc=gL, O_avg=avg, gradC=gradC, S=S, F=F, dw=dw,
                 C=np.mean(np.abs(Lloc) ** 2))
+
+
+def solve_minres_explicit(S, F, eps, tol, maxiter=None):
+    """MINRES (Paige & Saunders 1975) on A = S + eps I, x0 = 0, no preconditioner, stop when the recurrence residual
+    phibar <= tol ||F||.  The reference's sr_minres branch calls IterativeSolvers 0.8.1 `minres` (SRIterative.jl:101-125);
+    neither its iterates nor its iteration count are pinned by any reference test, so this restatement is only used
+    for the converged solution and an iteration-count sanity check.  Returns (x, iterations, converged)."""
+    A = np.asarray(S, dtype=np.complex128 if np.iscomplexobj(S) or np.iscomplexobj(F) else np.float64)
+    A = A + eps * np.eye(A.shape[0])
+    b = np.asarray(F, dtype=A.dtype)
+    P = b.size
+    maxiter = 10 * P if maxiter is None else maxiter
+    x = np.zeros(P, A.dtype)
+    r1 = np.zeros(P, A.dtype)
+    r2 = b.copy()
+    beta1 = np.sqrt(np.vdot(r2, r2).real)
+    if beta1 == 0.0:
+        return x, 0, True
+    oldb, beta, dbar, epsln, phibar, cs, sn = 0.0, beta1, 0.0, 0.0, beta1, -1.0, 0.0
+    wa, wb = np.zeros(P, A.dtype), np.zeros(P, A.dtype)
+    it = 0
+    while it < maxiter and not (phibar <= tol * beta1):
+        it += 1
+        v = r2 / beta
+        y = A @ v
+        if it >= 2:
+            y = y - (beta / oldb) * r1
+        alfa = np.vdot(v, y).real
+        y = y - (alfa / beta) * r2
+        r1, r2 = r2, y
+        oldb = beta
+        beta = np.sqrt(np.vdot(r2, r2).real)
+        oldeps, delta, gbar = epsln, cs * dbar + sn * alfa, sn * dbar - cs * alfa
+        epsln, dbar = sn * beta, -cs * beta
+        gamma = max(np.sqrt(gbar * gbar + beta * beta), 1e-300)
+        cs, sn = gbar / gamma, beta / gamma
+        phi = cs * phibar
+        phibar = sn * phibar
+        wn = (v - oldeps * wa - delta * wb) / gamma
+        x = x + phi * wn
+        wa, wb = wb, wn
+        if beta == 0.0:
+            break
+    return x, it, bool(phibar <= tol * beta1 or beta == 0.0)

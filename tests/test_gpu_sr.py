@@ -211,6 +211,45 @@ def test_matrix_free_cg(nq, ctx, dtype, real_params):
     assert np.linalg.norm(dw - np.linalg.solve(S + eps * np.eye(P), F)) <= 1e-7 * np.linalg.norm(ref)
 
 
+@pytest.mark.parametrize("dtype,real_params", [(np.complex128, False), (np.complex128, True), (np.float64, True)])
+def test_minres_explicit_and_matrix_free(nq, ctx, dtype, real_params):
+    """sr_minres (SRIterative.jl:101-125): MINRES on the explicit S and matrix-free, against the oracle's MINRES and a
+    direct solve (the reference pins neither iterates nor counts: converged solutions are compared)."""
+    import ctypes as C
+    L = nq._lib
+    rng = np.random.default_rng(18)
+    P, Ns = 150, 900
+    O = _rand(rng, (P, Ns), dtype)
+    O64 = O.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64)
+    _, Oc = OSR.center(O64)
+    cplx_out = np.dtype(dtype).kind == "c" and not real_params
+    F = rng.standard_normal(P) + (1j * rng.standard_normal(P) if cplx_out else 0)
+    eps = 0.01
+    S, _ = OSR.sr_setup(Oc, F, real_params)
+    direct = np.linalg.solve(S + eps * np.eye(P), F)
+    ref, it_ref, ok = OSR.solve_minres_explicit(S, F, eps, 1e-10)
+    assert ok and np.linalg.norm(ref - direct) <= 1e-8 * np.linalg.norm(direct)
+    # explicit S
+    Sw = np.asfortranarray(S.astype(np.complex128 if cplx_out else np.float64))
+    dw = np.zeros_like(F)
+    its = C.c_int64()
+    L.check(L.lib.nq_sr_solve(ctx.h, L.ptr(Sw), L.ptr(F), P, L.NQ_C128 if cplx_out else L.NQ_F64, eps, L.NQ_SOLVE_MINRES,
+                              1e-10, 0, L.ptr(dw), C.byref(its)), ctx.h)
+    assert np.linalg.norm(dw - direct) <= 1e-8 * np.linalg.norm(direct)
+    assert abs(its.value - it_ref) <= 2
+    # matrix-free
+    dOc = _dev(Oc.astype(dtype))
+    dw2 = np.zeros_like(F)
+    L.check(L.lib.nq_sr_solve_matfree_algo(ctx.h, dOc.data_ptr(), P, P, Ns, Ns, L.nq_dtype(dtype), L.ptr(F), int(real_params),
+                                           eps, L.NQ_SOLVE_MINRES, 1e-10, 0, L.ptr(dw2), C.byref(its)), ctx.h)
+    assert np.linalg.norm(dw2 - direct) <= 1e-7 * np.linalg.norm(direct)
+    assert abs(its.value - it_ref) <= 2
+    # exhausted iterations are reported like CG's
+    st = L.lib.nq_sr_solve_matfree_algo(ctx.h, dOc.data_ptr(), P, P, Ns, Ns, L.nq_dtype(dtype), L.ptr(F), int(real_params),
+                                        eps, L.NQ_SOLVE_MINRES, 1e-30, 3, L.ptr(dw2), C.byref(its))
+    assert st == L.NQ_ERR_NOT_CONVERGED and its.value == 3
+
+
 @pytest.mark.parametrize("dtype", [np.complex128, np.float64, np.complex64])
 def test_stat_analysis(nq, ctx, dtype):
     rng = np.random.default_rng(9)

@@ -155,3 +155,18 @@ def test_density_matrix_observable_estimator_is_trace_formula():
     loc = E.local_scalar_super(net, left, allS, allS)
     exact = np.trace(ops.to_matrix(O) @ rho) / np.trace(rho)
     assert abs(np.sum(p * loc) / p.sum() - exact) <= 1e-12 * max(1.0, abs(exact))
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_minres_restatement_converges_to_the_direct_solution(cplx):
+    rng = np.random.default_rng(3)
+    P = 80
+    X = rng.standard_normal((P, 3 * P)) + (1j * rng.standard_normal((P, 3 * P)) if cplx else 0)
+    S = X @ X.conj().T / (3 * P)
+    F = rng.standard_normal(P) + (1j * rng.standard_normal(P) if cplx else 0)
+    x, it, ok = sr.solve_minres_explicit(S, F, 1e-3, 1e-12)
+    ref = np.linalg.solve(S + 1e-3 * np.eye(P), F)
+    assert ok and 0 < it <= 10 * P
+    assert np.linalg.norm(x - ref) <= 1e-9 * np.linalg.norm(ref)
+    x3, it3, ok3 = sr.solve_minres_explicit(S, F, 1e-3, 1e-30, maxiter=3)
+    assert it3 == 3 and not ok3
