@@ -9,7 +9,7 @@ from .operators import (LocalOperator as _LocalOperator, KLocalOperatorRow, Liou
                         sigmaz, sigmam, sigmap, destroy, create, number, DeviceOperator)
 from .machines import RBM, RBMSplit, NDM, af_softplus, af_logcosh, init_random_pars_
 from .samplers import MetropolisSampler, MetropolisSamplerCache, LocalRule
-from .algorithms import (SR, Descent, update_, local_scalar, local_grad, stat_analysis, Measurement, sr_cholesky,
+from .algorithms import (SR, Descent, Nesterov, update_, local_scalar, local_grad, stat_analysis, Measurement, sr_cholesky,
                          sr_cg, sr_minres)
 from .iterative import BatchedSampler, BatchedObsDMSampler
 from .parallel import shard_chains, init_comm, world_from_env

@@ -81,5 +81,29 @@ class Descent:
         self.eta = eta
 
 
+    def step(self, dw, state=None):
+        """(delta, eta) such that w <- w - eta * delta."""
+        return dw, self.eta
+
+
+class Nesterov:
+    """Optimisers.Nesterov(lr, mu) (rules.jl:36-55): v is the velocity kept per parameter vector,
+        d = mu^2 v - (1 + mu) lr dw;   v <- mu v - lr dw;   w <- w + d.
+    The velocity lives with the optimiser object (the reference keys an IdDict by the parameter array)."""
+
+    def __init__(self, lr=0.1, mu=0.9, gclip=0.0):
+        self.lr, self.mu, self.gclip = float(lr), float(mu), float(gclip)
+        self.eta = 1.0
+        self.v = None
+
+    def step(self, dw, state=None):
+        if self.v is None or self.v.shape != dw.shape:
+            self.v = dw * 0
+        d = (self.mu ** 2) * self.v - (1.0 + self.mu) * self.lr * dw
+        self.v = self.mu * self.v - self.lr * dw
+        return -d, 1.0                      # w <- w - 1 * (-d)
+
+
 def update_(opt, net, dw):
-    net.update(dw, opt.eta)
+    delta, eta = opt.step(np.asarray(dw))
+    net.update(delta, eta)

@@ -203,9 +203,11 @@ class BatchedSampler:
     def update_(self, opt, dw=None):
         dw = self.dw if dw is None else dw
         net = self.net
-        if dw.dtype != _tdtype(net.dtype):
-            dw = dw.to(_tdtype(net.dtype))
-        L.check(L.lib.nq_update(net.h, dw.data_ptr(), float(opt.eta)), self.ctx.h)
+        delta, eta = opt.step(dw)               # Descent: (dw, eta); Nesterov: velocity update on the device tensor
+        if delta.dtype != _tdtype(net.dtype):
+            delta = delta.to(_tdtype(net.dtype))
+        delta = delta.contiguous()
+        L.check(L.lib.nq_update(net.h, delta.data_ptr(), float(eta)), self.ctx.h)
 
 
 class BatchedObsDMSampler:

@@ -145,3 +145,24 @@ def test_ket_observables_on_stored_samples(nq, ctx):
         m = res[name]
         assert abs(m.mean - ref["mean"]) <= 1e-11 * max(1.0, abs(ref["mean"])), name
         assert abs(m.error - ref["error"]) <= 1e-9 * max(1e-3, ref["error"]), name
+
+
+def test_nesterov_update_rule(nq, ctx):
+    """Optimisers.Nesterov (rules.jl:36-55): d = mu^2 v - (1+mu) lr dw, v <- mu v - lr dw, w <- w + d."""
+    import torch
+    N = 6
+    om, pm, hilb = H.make_pair(nq, ctx, "rbm", "spin", N, 2, np.complex128, OM.LOGCOSH)
+    ph, pH = H.p_tfim_1d(nq, N)
+    bs = nq.BatchedSampler(pm, nq.MetropolisSampler(nq.LocalRule(), 4, N, burn=2, seed=3), pH,
+                           nq.SR(np.float32, eps=0.1, algorithm="sr_cholesky"), batch_sz=4)
+    opt = nq.Nesterov(0.05, 0.9)
+    rng = np.random.default_rng(2)
+    w = pm.params().astype(np.complex128)
+    v = np.zeros_like(w)
+    for it in range(3):
+        g = rng.standard_normal(pm.P) + 1j * rng.standard_normal(pm.P)
+        bs.update_(opt, torch.from_numpy(g).cuda())
+        d = 0.81 * v - 1.9 * 0.05 * g
+        v = 0.9 * v - 0.05 * g
+        w = w + d
+        H.assert_close(pm.params(), w, 1e-13, "Nesterov step %d" % it)
