@@ -1387,6 +1387,7 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
             if (waves >= 1.0 || ns == 1) { if (cost < best) { best = cost; nsplit = ns; } }
         }
     }
+    if (const char* e = getenv("NQ_SYRK_NSPLIT")) { int v = atoi(e); if (v >= 1 && v <= 64 && nchunk / v >= 1) nsplit = v; }   // tuning knob
     const int64_t ldr = ldO * (ocx ? 2 : 1);
     // FP32 mode: tcgen05 3xTF32 path (nq_syrk_tf32.cu) when the rows allow 16-byte loads
     static const bool fp32_dmma = [] { const char* e = getenv("NQ_SR_FP32_PATH"); return e && !strcmp(e, "dmma"); }();
