@@ -8,7 +8,7 @@ from .core import Context, HomogeneousSpin, HomogeneousFock, Hilbert, unique_id
 from .operators import (LocalOperator as _LocalOperator, KLocalOperatorRow, Liouvillian, liouvillian, sigmax, sigmay,
                         sigmaz, sigmam, sigmap, destroy, create, number, DeviceOperator)
 from .machines import RBM, RBMSplit, NDM, af_softplus, af_logcosh, init_random_pars_
-from .samplers import MetropolisSampler, MetropolisSamplerCache, LocalRule
+from .samplers import MetropolisSampler, MetropolisSamplerCache, LocalRule, ExactSampler, ExactSamplerCache
 from .algorithms import (SR, Descent, Nesterov, update_, local_scalar, local_grad, stat_analysis, Measurement, sr_cholesky,
                          sr_cg, sr_minres)
 from .iterative import BatchedSampler, BatchedObsDMSampler

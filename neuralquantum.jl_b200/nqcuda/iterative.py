@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib as L
 from .algorithms import Measurement, SR, sr_cg, sr_cholesky, sr_minres, stat_analysis
 from .operators import Liouvillian
-from .samplers import MetropolisSamplerCache
+from .samplers import ExactSampler, ExactSamplerCache, MetropolisSamplerCache
 
 
 def _torch():
@@ -46,8 +46,8 @@ class BatchedSampler:
         self.op = problem.to_device(ctx)
         self.nranks, self.rank = ctx.comm_size()
         self.B = int(batch_sz)
-        self.cache = MetropolisSamplerCache(sampler, net, self.B, chain_offset=self.rank * self.B,
-                                            num_workers=self.nranks)
+        cache_type = ExactSamplerCache if isinstance(sampler, ExactSampler) else MetropolisSamplerCache
+        self.cache = cache_type(sampler, net, self.B, chain_offset=self.rank * self.B, num_workers=self.nranks)
         self.L = self.cache.loc_chain_length if chain_length is None else int(chain_length)
         self.Ns = self.B * self.L
         self.Ns_total = self.Ns * self.nranks
@@ -77,6 +77,9 @@ class BatchedSampler:
     # ---- the hot path -----------------------------------------------------------------
     def sample_states(self):
         """_sample_state!: re-randomise the chains, burn, fill the L slices."""
+        if isinstance(self.cache, ExactSamplerCache):
+            self.cache.sample_into(self.L, self.prow, self.pcol)
+            return
         self.cache.randomize()
         self.cache.sample(self.sampler.burn_length, self.L,
                           packed_out=(self.prow.data_ptr(), self.pcol.data_ptr() if self.pcol is not None else None))

@@ -91,3 +91,66 @@ class MetropolisSamplerCache:
         a, b = C.c_int64(), C.c_int64()
         L.check(L.lib.nq_sampler_counters(self.h, C.byref(a), C.byref(b)), self.net.ctx.h)
         return a.value, b.value
+
+
+class ExactSampler:
+    """ExactSampler(n_samples; seed) (Samplers/Exact.jl:3-21): builds the full probability table of the state and
+    samples it exactly.  Indexable spaces only -- 2^N (ket) or 4^N (density matrix) table entries."""
+
+    def __init__(self, n_samples, seed=None):
+        self.samples_length = int(n_samples)
+        self.chain_length = self.samples_length
+        self.burn_length = 0
+        self.seed = int(np.random.SeedSequence().entropy % (1 << 63)) if seed is None else int(seed)
+
+
+class ExactSamplerCache:
+    """Exact.jl:135-181 on the device: log-probabilities of ALL basis states through the machine kernel (packed
+    index = basis number: site 1 is the least significant digit, super-index = col * D + row), a cumulative table,
+    and one independent inverse-CDF draw per (chain, slot).  The table and the draws use torch ops: this is the
+    reference's validation sampler, not part of the hot path.  Julia's MersenneTwister stream is not reproduced."""
+    MAX_TABLE = 1 << 24
+
+    def __init__(self, sampler, net, batch_sz, chain_offset=0, num_workers=1):
+        import torch
+        if net.N > 62:
+            raise ValueError("ExactSampler needs an indexable space")
+        self.s, self.net, self.B = sampler, net, int(batch_sz)
+        self.loc_chain_length = -(-sampler.samples_length // num_workers)            # Exact.jl:41
+        self.D = 1 << net.N
+        self.size = self.D * self.D if net.doubled else self.D
+        if self.size > self.MAX_TABLE:
+            raise ValueError("ExactSampler: %d table entries (Closed N < 24, Open N < 12)" % self.size)
+        self.gen = torch.Generator(device="cuda")
+        self.gen.manual_seed((sampler.seed + 0x9E3779B97F4A7C15 * (chain_offset + 1)) % (1 << 63))
+        self.cdf = None
+
+    def init_sampler(self):
+        """init_sampler!: the probability table of the CURRENT parameters."""
+        import torch
+        net, dev = self.net, torch.device("cuda", self.net.ctx.device)
+        idx = torch.arange(self.size, dtype=torch.int64, device=dev)
+        row = (idx % self.D).contiguous() if net.doubled else idx
+        col = (idx // self.D).contiguous() if net.doubled else None
+        from .iterative import _tdtype
+        out = torch.zeros(self.size, dtype=_tdtype(net.out_dtype), device=dev)
+        L.check(L.lib.nq_logpsi_packed(net.h, row.data_ptr(), col.data_ptr() if col is not None else None, self.size,
+                                       out.data_ptr()), net.ctx.h)
+        lp = 2.0 * out.real.to(torch.float64) if out.is_complex() else 2.0 * out.to(torch.float64)   # log_prob_psi
+        p = torch.exp(lp - lp.max())
+        self.cdf = torch.cumsum(p, 0)
+        self.cdf /= self.cdf[-1].clone()
+        return self.cdf
+
+    def sample_into(self, L_store, prow, pcol):
+        """samplenext! for every (slot, chain): basis number by inverse CDF, written as packed words [L, B, 1]."""
+        import torch
+        self.init_sampler()
+        u = torch.rand((L_store, self.B), generator=self.gen, device=self.cdf.device, dtype=torch.float64)
+        hi = torch.searchsorted(self.cdf, u.reshape(-1)).clamp_(max=self.size - 1).reshape(L_store, self.B)
+        if self.net.doubled:
+            prow[:, :, 0] = hi % self.D
+            pcol[:, :, 0] = hi // self.D
+        else:
+            prow[:, :, 0] = hi
+        return hi

@@ -126,3 +126,49 @@ def test_production_density_matrix_and_sharding_invariance(nq, ctx):
         part.randomize()
         pr, pc = part.sample()
         assert np.array_equal(pr, sr[:, off:off + 32]) and np.array_equal(pc, sc[:, off:off + 32])
+
+
+def test_exact_sampler_ket_and_density_matrix(nq, ctx):
+    """ExactSampler (Samplers/Exact.jl): inverse-CDF draws from the full probability table; chi-square against the
+    oracle's |psi|^2 / |rho|^2 and a sampled energy within a few standard errors of exact diagonalisation."""
+    import torch
+    from oracle import operators as OO
+    from oracle.models import tfim_1d
+    N = 5
+    om, pm, hilb = H.make_pair(nq, ctx, "rbm", "spin", N, 2, np.complex128, OM.LOGCOSH, seed=3, std=0.3)
+    oh, oH = tfim_1d(N)
+    ph, pH = H.p_tfim_1d(nq, N)
+    bs = nq.BatchedSampler(pm, nq.ExactSampler(200, seed=5), pH, nq.SR(np.float32, eps=0.1), batch_sz=64)
+    stat, _ = bs.sample_()
+    codes = bs.prow.cpu().numpy().ravel()
+    allS = H.ohilb("spin", N).all_states()
+    code_of = (((allS + 1) / 2).astype(int) * (1 << np.arange(N))[:, None]).sum(0)
+    psi = np.exp(om.logpsi(allS))
+    p = np.abs(psi) ** 2
+    p /= p.sum()
+    pk = np.zeros(1 << N)
+    pk[code_of] = p
+    cnt = np.bincount(codes, minlength=1 << N)
+    assert cnt.sum() == 200 * 64
+    exp = pk * cnt.sum()
+    big = exp >= 5                       # pool the bins whose expected count is too small for the chi-square statistic
+    obs_p = np.append(cnt[big], cnt[~big].sum())
+    exp_p = np.append(exp[big], exp[~big].sum())
+    assert sst.chisquare(obs_p, exp_p).pvalue >= 0.01
+    Hm = OO.to_matrix(oH)
+    exact = (psi.conj() @ (Hm @ psi) / (psi.conj() @ psi)).real
+    assert abs(stat.mean.real - exact) <= 6 * max(stat.error, 1e-3)
+    # density matrix: joint (row, col) index
+    N2 = 2
+    om2, pm2, hilb2 = H.make_pair(nq, ctx, "ndm", "fock", N2, 2, np.float64, OM.SOFTPLUS, seed=123, std=0.3)
+    _, _, _, pl = H.p_lindblad_ising_1d(nq, N2)
+    bs2 = nq.BatchedSampler(pm2, nq.ExactSampler(300, seed=7), pl, nq.SR(np.float32, eps=0.001), batch_sz=32)
+    bs2.sample_states()
+    joint = bs2.prow.cpu().numpy().ravel() + 4 * bs2.pcol.cpu().numpy().ravel()
+    allS2 = H.ohilb("fock", N2).all_states()
+    R = np.stack([allS2[:, k % 4] for k in range(16)], 1)
+    Cc = np.stack([allS2[:, k // 4] for k in range(16)], 1)
+    p2 = np.abs(np.exp(om2.logpsi(R, Cc))) ** 2
+    p2 /= p2.sum()
+    cnt2 = np.bincount(joint, minlength=16)
+    assert sst.chisquare(cnt2, p2 * cnt2.sum()).pvalue >= 0.01
