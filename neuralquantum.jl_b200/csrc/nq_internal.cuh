@@ -48,6 +48,12 @@ struct nq_operator_s {
     // flat records (N <= 64): [n_recs][8] = rmask, rval, cmask, cval, rflip, cflip, mel_re, mel_im (doubles as bits)
     uint64_t* recs;
     int n_recs;
+    // site tables (site-local operators, N <= 64): the summed matrix element of every (site, pattern) slot and of the
+    // diagonal as lookup tables over the few configuration bits it depends on; see build_site_luts (nq_operator.cu)
+    int32_t* lut_units;     // [n_lut_units][2] group range of a unit; units 0..3N-1 = slots 3 j + pattern, then diagonal units
+    uint64_t* lut_groups;   // [n_groups][2] = (8 bit selectors: side << 6 | site, 0xFF unused ; table offset)
+    double* lut_tab;        // complex128 entries
+    int n_lut_units;
 };
 
 // device-pointer internals shared between translation units

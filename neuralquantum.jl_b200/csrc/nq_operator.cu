@@ -29,6 +29,10 @@ struct OpDev {
     const int32_t* term_right;
     const uint64_t* recs;   // flat (condition, flips, mel) records, see nq_operator_create
     int n_recs;
+    const int2* lut_units;  // site tables, see build_site_luts
+    const ulonglong2* lut_groups;
+    const double2* lut_tab;
+    int n_lut_units;
 };
 
 OpDev op_dev(nq_operator_t op) {
@@ -38,6 +42,8 @@ OpDev op_dev(nq_operator_t op) {
     d.part_row0 = op->part_row0; d.row_ptr = op->row_ptr; d.entry_mel = op->entry_mel;
     d.entry_flip = op->entry_flip; d.term_left = op->term_left; d.term_right = op->term_right;
     d.recs = op->recs; d.n_recs = op->n_recs;
+    d.lut_units = (const int2*)op->lut_units; d.lut_groups = (const ulonglong2*)op->lut_groups;
+    d.lut_tab = (const double2*)op->lut_tab; d.n_lut_units = op->n_lut_units;
     return d;
 }
 
@@ -206,6 +212,7 @@ __device__ inline unsigned char* conn_list_carve(unsigned char* p, int cap, int 
 
 #include "nq_estimators.inc"
 #include "nq_estimators_ndm3.inc"
+#include "nq_estimators_ndm4.inc"
 
 }  // namespace
 
@@ -224,6 +231,18 @@ int nq_local_device(nq_machine_t m, nq_operator_t op, const uint64_t* pr, const 
     NQ_CHECK(nq_machine_ensure_tables(m));
     if (m->kind == NQ_NDM) {
         bool used = false;
+        // v4 (warp per configuration) where it applies, else v3t / the list kernel; NQ_NDM_KERNEL=v3 forces the latter
+        const char* envk = getenv("NQ_NDM_KERNEL");
+        if (!(envk && !strcmp(envk, "v3"))) {
+            if (m->dtype == NQ_F64) {
+                NQ_CHECK((m->act == NQ_SOFTPLUS ? launch_local_ndm4<double, NQ_SOFTPLUS>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)
+                                                 : launch_local_ndm4<double, NQ_LOGCOSH>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)));
+            } else {
+                NQ_CHECK((m->act == NQ_SOFTPLUS ? launch_local_ndm4<float, NQ_SOFTPLUS>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)
+                                                 : launch_local_ndm4<float, NQ_LOGCOSH>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)));
+            }
+            if (used) return NQ_OK;
+        }
         if (m->dtype == NQ_F64) {
             NQ_CHECK((m->act == NQ_SOFTPLUS ? launch_local_ndm3<double, NQ_SOFTPLUS>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)
                                              : launch_local_ndm3<double, NQ_LOGCOSH>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)));
@@ -260,13 +279,86 @@ static int upload(nq_ctx_t ctx, X** dst, const X* src, size_t n) {
     return NQ_OK;
 }
 
+
+// Site tables for site-local operators (N <= 64).  Every flat record contributes its matrix element to one slot:
+// the diagonal, or (site j, pattern p) with p = 0 flip on sigma, 1 flip on sigma', 2 flip on both.  The records of a
+// slot are cut into groups whose conditions read at most LUT_BITS configuration bits; a group becomes a table
+// indexed by those bits holding the sum (in record = reference order) of the matching matrix elements.  A
+// configuration then costs one bit gather and one 16-byte load per group instead of a pass over all records.
+// Diagonal groups are independent units (summed across lanes), the groups of an off-diagonal slot form one unit.
+static constexpr int LUT_BITS = 8;
+static int build_site_luts(nq_ctx_t ctx, nq_operator_t op, const std::vector<uint64_t>& recs, int N) {
+    struct Rec { uint64_t rm, rv, cm, cv; double mr, mi; };
+    struct Group { uint64_t rmask = 0, cmask = 0; std::vector<Rec> recs; };
+    const int n_slots = 3 * N + 1, diag = 3 * N;
+    std::vector<std::vector<Group>> slots(n_slots);
+    auto popc = [](uint64_t x) { return __builtin_popcountll(x); };
+    for (size_t r = 0; r + 8 <= recs.size(); r += 8) {
+        const uint64_t rf = recs[r + 4], cf = recs[r + 5];
+        Rec rec{recs[r], recs[r + 1], recs[r + 2], recs[r + 3], 0.0, 0.0};
+        memcpy(&rec.mr, &recs[r + 6], 8); memcpy(&rec.mi, &recs[r + 7], 8);
+        int slot = diag;
+        if (rf | cf) {
+            if (popc(rf) > 1 || popc(cf) > 1 || (rf && cf && rf != cf)) return NQ_OK;     // not site-local: no tables
+            slot = 3 * __builtin_ctzll(rf | cf) + ((rf ? 1 : 0) + (cf ? 2 : 0) - 1);
+        }
+        if (popc(rec.rm) + popc(rec.cm) > LUT_BITS) return NQ_OK;
+        auto& gs = slots[slot];
+        Group* g = nullptr;
+        for (auto& cand : gs)          // first group whose support stays within LUT_BITS bits
+            if (popc(cand.rmask | rec.rm) + popc(cand.cmask | rec.cm) <= LUT_BITS) { g = &cand; break; }
+        if (!g) { gs.emplace_back(); g = &gs.back(); }
+        g->rmask |= rec.rm; g->cmask |= rec.cm;
+        g->recs.push_back(rec);
+    }
+    std::vector<int32_t> units;
+    std::vector<uint64_t> groups;
+    std::vector<double> tab;
+    auto emit_group = [&](const Group& g) {
+        int pos[LUT_BITS], nb = 0;
+        for (int side = 0; side < 2; side++) {
+            const uint64_t mk = side ? g.cmask : g.rmask;
+            for (int b = 0; b < 64; b++) if ((mk >> b) & 1ull) pos[nb++] = (side << 6) | b;
+        }
+        uint64_t sel = 0;
+        for (int i = 0; i < LUT_BITS; i++) sel |= (uint64_t)(i < nb ? pos[i] : 0xFF) << (8 * i);
+        groups.push_back(sel);
+        groups.push_back((uint64_t)(tab.size() / 2));
+        for (int idx = 0; idx < (1 << nb); idx++) {
+            uint64_t rb = 0, cb = 0;
+            for (int i = 0; i < nb; i++) if ((idx >> i) & 1) ((pos[i] & 64) ? cb : rb) |= 1ull << (pos[i] & 63);
+            double sr = 0.0, si = 0.0;
+            for (const Rec& rec : g.recs)
+                if ((rb & rec.rm) == rec.rv && (cb & rec.cm) == rec.cv) { sr += rec.mr; si += rec.mi; }
+            tab.push_back(sr); tab.push_back(si);
+        }
+    };
+    for (int slot = 0; slot < diag; slot++) {
+        units.push_back((int32_t)(groups.size() / 2));
+        for (const Group& g : slots[slot]) emit_group(g);
+        units.push_back((int32_t)(groups.size() / 2));
+    }
+    for (const Group& g : slots[diag]) {
+        units.push_back((int32_t)(groups.size() / 2));
+        emit_group(g);
+        units.push_back((int32_t)(groups.size() / 2));
+    }
+    if (tab.size() > ((size_t)1 << 22)) return NQ_OK;
+    int s;
+    if ((s = upload(ctx, &op->lut_units, units.data(), units.size())) != NQ_OK) return s;
+    if ((s = upload(ctx, &op->lut_groups, groups.data(), groups.size())) != NQ_OK) return s;
+    if ((s = upload(ctx, &op->lut_tab, tab.data(), tab.size())) != NQ_OK) return s;
+    op->n_lut_units = (int)(units.size() / 2);
+    return NQ_OK;
+}
+
 extern "C" int nq_operator_destroy(nq_operator_t op) {
     if (!op) return NQ_ERR_ARG;
     cudaSetDevice(op->ctx->device);
     cudaStreamSynchronize(op->ctx->stream);
     cudaFree(op->part_nsites); cudaFree(op->part_site_ptr); cudaFree(op->part_sites); cudaFree(op->part_row0);
     cudaFree(op->row_ptr); cudaFree(op->entry_mel); cudaFree(op->entry_flip); cudaFree(op->term_left); cudaFree(op->term_right);
-    cudaFree(op->recs);
+    cudaFree(op->recs); cudaFree(op->lut_units); cudaFree(op->lut_groups); cudaFree(op->lut_tab);
     delete op;
     return NQ_OK;
 }
@@ -395,6 +487,7 @@ extern "C" int nq_operator_create(nq_ctx_t ctx, nq_space space, int N, int n_par
         if (flat && !recs.empty()) {
             if ((s = upload(ctx, &op->recs, recs.data(), (int64_t)recs.size())) != NQ_OK) { nq_operator_destroy(op); return s; }
             op->n_recs = (int)(recs.size() / 8);
+            if (site_local && (s = build_site_luts(ctx, op, recs, N)) != NQ_OK) { nq_operator_destroy(op); return s; }
         }
         *out = op;
         return NQ_OK;
