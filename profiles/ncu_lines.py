@@ -11,6 +11,8 @@ import tempfile
 
 rep, rx, obj, mangled = sys.argv[1:5]
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
+by_ins = len(sys.argv) > 6 and "ins" in sys.argv[6]     # sort by executed instructions instead of samples
+outer = len(sys.argv) > 6 and "outer" in sys.argv[6]    # attribute inlined code to the outermost call site (nvdisasm -gi)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + rx], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 h = rows[1]
@@ -25,7 +27,7 @@ base = ins[0][0]
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
 cub = glob.glob(os.path.join(tmp, "*.cubin"))[0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout.splitlines()
+dis = subprocess.run(["nvdisasm", "-gi" if outer else "-g", "-c", cub], capture_output=True, text=True).stdout.splitlines()
 line_of = {}
 cur, infunc = None, False
 for l in dis:
@@ -36,6 +38,7 @@ for l in dis:
         continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m:
+        # with -gi a chain "X inlined at Y" precedes the instruction; its last line is the outermost frame
         cur = (os.path.basename(m.group(1)), int(m.group(2)))
         continue
     m = re.match(r"\s*/\*([0-9a-f]+)\*/", l)
@@ -51,7 +54,7 @@ for addr, ns, ne, st, txt in ins:
 tot_s, tot_e = sum(a[0] for a in agg.values()), sum(a[1] for a in agg.values())
 print("samples", tot_s, "warp-instr", tot_e, "instructions", len(ins))
 srcs = {}
-for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][1 if by_ins else 0])[:top]:
     if f not in srcs:
         cand = glob.glob(os.path.join(os.path.dirname(os.path.abspath(obj)), "..", "csrc", f))
         srcs[f] = open(cand[0]).read().splitlines() if cand else []
