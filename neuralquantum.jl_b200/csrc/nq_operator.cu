@@ -212,7 +212,6 @@ __device__ inline unsigned char* conn_list_carve(unsigned char* p, int cap, int 
 
 #include "nq_estimators.inc"
 #include "nq_estimators_ndm3.inc"
-#include "nq_estimators_ndm4.inc"
 #include "nq_estimators_ndm5.inc"
 
 }  // namespace
@@ -232,7 +231,7 @@ int nq_local_device(nq_machine_t m, nq_operator_t op, const uint64_t* pr, const 
     NQ_CHECK(nq_machine_ensure_tables(m));
     if (m->kind == NQ_NDM) {
         bool used = false;
-        // v4 (warp per configuration) where it applies, else v3t / the list kernel; NQ_NDM_KERNEL=v3 forces the latter
+        // v5 (warp per configuration) where it applies, else v3t / the list kernel; NQ_NDM_KERNEL=v3 forces the latter
         const char* envk = getenv("NQ_NDM_KERNEL");
         if (!envk || !strcmp(envk, "v5")) {
             if (m->dtype == NQ_F64) {
@@ -241,16 +240,6 @@ int nq_local_device(nq_machine_t m, nq_operator_t op, const uint64_t* pr, const 
             } else {
                 NQ_CHECK((m->act == NQ_SOFTPLUS ? launch_local_ndm5<float, NQ_SOFTPLUS>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)
                                                  : launch_local_ndm5<float, NQ_LOGCOSH>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)));
-            }
-            if (used) return NQ_OK;
-        }
-        if (!(envk && !strcmp(envk, "v3"))) {
-            if (m->dtype == NQ_F64) {
-                NQ_CHECK((m->act == NQ_SOFTPLUS ? launch_local_ndm4<double, NQ_SOFTPLUS>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)
-                                                 : launch_local_ndm4<double, NQ_LOGCOSH>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)));
-            } else {
-                NQ_CHECK((m->act == NQ_SOFTPLUS ? launch_local_ndm4<float, NQ_SOFTPLUS>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)
-                                                 : launch_local_ndm4<float, NQ_LOGCOSH>(m, op, pr, pc, B, out_logpsi, O, ldO, out_loc, out_g, ld, &used)));
             }
             if (used) return NQ_OK;
         }
