@@ -24,7 +24,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "neuralquantum.jl_b200"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "neuralquantum.jl_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -109,7 +109,16 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-NCU_FUSED_DRAM_BYTES = 4.5096e9   # local_ndm3t_kernel<double>, cfg4, 65536 configurations per launch
+def ncu_fused_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused kernel on the cfg4 batch, taken from the
+    committed `ncu --set full` capture (profiles/ncu_traffic.py writes the file); None when the file is absent."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r2_fused_kernel_traffic.json")))
+        return float(rec["dram_bytes"]), rec.get("report")
+    except Exception:
+        return None, None
+
+
 _REAL_STDOUT = None
 
 
@@ -177,6 +186,50 @@ class ClockSampler:
         return out
 
 
+def multi_gpu_parity(nq, torch, dist, ctx, net, liouv, world, rank, local, n_sub=4096):
+    """Cross-rank check of the exchange steps on a 4096-sample subset of the workload: the sharded iteration
+    (all-reduced <O>, F, S; replicated solve) against a SINGLE-RANK recomputation of the same samples on rank 0 (second
+    context without a communicator), and bit-equality of the update across ranks.  ref: Parallel/MPI/mpi.jl:21-74."""
+    w = WORKLOAD
+    N, Lc = w["N"], w["L"]
+    Bt = n_sub // Lc
+    Bt -= Bt % world
+    rng = np.random.Generator(np.random.Philox(777))          # same subset on every rank
+    R = rng.integers(0, 2, size=(N, Bt, Lc)).astype(np.float64)
+    Cc = rng.integers(0, 2, size=(N, Bt, Lc)).astype(np.float64)
+    B = Bt // world
+    sl = slice(rank * B, (rank + 1) * B)
+    algo = nq.SR(np.float32, eps=w["eps"], algorithm="sr_cholesky")
+    smp = nq.MetropolisSampler(nq.LocalRule(), Lc * world, w["passes"] - 1, burn=1, seed=5)
+    bs = nq.BatchedSampler(net, smp, liouv, algo, batch_sz=B, chain_length=Lc)
+    bs.set_samples((np.asfortranarray(R[:, sl]), np.asfortranarray(Cc[:, sl])))
+    stat, _ = bs.sample_(sample=False)
+    S_sh, F_sh = bs.S.clone(), bs.F.clone()
+    dw_sh = bs.precondition_().clone()
+    lo, hi = dw_sh.clone(), dw_sh.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out = {"samples": int(Bt * Lc), "dw_bit_identical_across_ranks": bool(torch.equal(lo, hi))}
+    if rank == 0:
+        ctx1 = nq.Context(local, torch.cuda.current_stream().cuda_stream)     # no communicator: NotParallel
+        net1 = nq.NDM(ctx1, net.hilb, np.float64, w["alpha"], w["alpha"], nq.af_softplus, seed=1234)
+        net1.set_params(net.params())
+        b1 = nq.BatchedSampler(net1, smp, liouv, algo, batch_sz=Bt, chain_length=Lc)
+        b1.set_samples((np.asfortranarray(R), np.asfortranarray(Cc)))
+        stat1, _ = b1.sample_(sample=False)
+
+        def rel(a, b):
+            return float((torch.linalg.norm((a - b).reshape(-1)) / torch.linalg.norm(b.reshape(-1))).item())
+        out["S_rel"], out["F_rel"] = rel(S_sh, b1.S), rel(F_sh, b1.F)
+        out["dw_rel"] = rel(dw_sh, b1.precondition_())
+        out["cost_rel"] = abs(stat.mean - stat1.mean) / abs(stat1.mean)
+        out["stat_error_rel"] = abs(stat.error - stat1.error) / abs(stat1.error)
+        out["max_rel"] = max(out["S_rel"], out["F_rel"], out["dw_rel"], out["cost_rel"], out["stat_error_rel"])
+        out["tolerance"] = "1e-11 on S, F, cost; dw up to the conditioning of S + eps I"
+    dist.barrier()
+    return out
+
+
 def run_gpu(args):
     # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -184,7 +237,6 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     import nqcuda as nq
-    import helpers as H
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -206,7 +258,7 @@ def run_gpu(args):
     B = w["chains"] // world                       # chains of this rank (strong scaling)
     Ns = B * Lc
     Ns_global = Ns * world
-    hilb, _, _, liouv = H.p_lindblad_ising_1d(nq, N, w["g"], w["V"])
+    hilb, _, _, liouv = nq.models.lindblad_ising_1d(N, w["g"], w["V"])
     net = nq.NDM(ctx, hilb, np.float64, w["alpha"], w["alpha"], nq.af_softplus, seed=1234)
     nq.init_random_pars_(net, sigma=0.01, seed=1234)
     smp = nq.MetropolisSampler(nq.LocalRule(), Lc * world, w["passes"] - 1, burn=w["burn"], seed=99)
@@ -330,6 +382,7 @@ def run_gpu(args):
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = Ns_global * args.steps / (ms_e2e * 1e-3)
     clk = clocks.stop()      # sampled over every timed region above (headline, per-kernel, SR iteration, e2e)
+    parity = multi_gpu_parity(nq, torch, dist, ctx, net, liouv, world, rank, local) if world > 1 else None
 
     if rank != 0:
         if world > 1:
@@ -340,16 +393,17 @@ def run_gpu(args):
     bytes_eval = Ns * (P * es + es + 2 * 8)               # O row + log rho + two packed words per configuration
     bytes_fused = Ns * (2 * P * es + 2 * es + 2 * 8)      # O row + grad L_loc row + log rho + L_loc + packed words
     ach = bytes_fused / (t_loc * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "local_ndm3t_kernel<double,softplus,grad,with_O> (fused eval+grad+estimator)",
+    traffic, traffic_src = ncu_fused_traffic()
+    roof = {"bound": "hbm", "kernel": "local_ndm5_kernel<double,softplus,grad,with_O> (fused eval+grad+estimator)",
             "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r1k_top_kernels.txt)
-            "traffic": NCU_FUSED_DRAM_BYTES if (world == 1 and Ns == 65536) else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this batch (ncu --set full)
+            "traffic": traffic if (world == 1 and Ns == 65536) else None, "traffic_source": traffic_src,
             "peak_source": pk_kind, "ms_per_launch": t_loc, "algorithmic_bytes_per_launch": bytes_fused,
-            "note": "the kernel is FP64-issue bound, not HBM bound: see DESIGN.md section 4",
+            "note": "write-bound: DRAM traffic = algorithmic bytes; remaining gap is instruction issue, DESIGN.md section 4",
             "all": {"ndm_evalgrad_kernel (stand-alone nq_logpsi_grad)": {
                         "ms": t_eval, "GB/s": bytes_eval / (t_eval * 1e-3) / 1e9,
                         "frac": bytes_eval / (t_eval * 1e-3) / 1e9 / pk["hbm_gbs"]},
-                    "local_ndm3t_kernel (fused)": {"ms": t_loc, "GB/s": ach, "frac": ach / pk["hbm_gbs"]},
+                    "local_ndm5_kernel (fused)": {"ms": t_loc, "GB/s": ach, "frac": ach / pk["hbm_gbs"]},
                     "syrk_dmma2_kernel (S assembly, nq_sr_setup)": {
                         "bound": "tensor", "ms": t_setup, "achieved": flops_setup / (t_setup * 1e-3) / 1e12, "unit": "TFLOP/s",
                         "peak": FP64_TENSOR_PEAK, "frac": flops_setup / (t_setup * 1e-3) / 1e12 / FP64_TENSOR_PEAK,
@@ -363,7 +417,7 @@ def run_gpu(args):
                        "l2": "every step writes O and grad L_loc (%.2f GB per GPU) >> 126 MB L2" % (2 * Ns * P * es / 1e9)},
             "sr_iteration": {"value": ms_sr * 1e-3 / n_it, "unit": "s", "iterations": n_it, "phases_ms": phases,
                              "includes": "sampler(burn=100,passes=17)+eval/grad+estimator+centre+force+S(+allreduce)+Cholesky+update"},
-            "roofline": roof, "clocks": clk, "gpu_launches": int(launches),
+            "roofline": roof, "clocks": clk, "gpu_launches": int(launches), "parity": parity,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(2 * Ns * N * 8),
                     "d2h_bytes_per_step": int(Ns * 16), "ms_per_step": ms_e2e / args.steps}}
     if world == 1 and not args.no_cpu:

@@ -245,7 +245,9 @@ int nq_sr_solve_matfree_algo(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t 
  * ref: Optimisers/rules.jl:11-17, apply.jl:25-73 */
 int nq_update(nq_machine_t m, const void* dw, double eta);
 /* stat_analysis over [B chains, L] values (column-major [B,L]); out = {mean_re, mean_im, error,
- * variance, tau, R} host doubles.  vdtype: NQ_F32/F64/C64/C128.  ref: utils/stats.jl:26-50 */
+ * variance, tau, R} host doubles.  vdtype: NQ_F32/F64/C64/C128.  ref: utils/stats.jl:26-50.
+ * With a communicator the statistics are those of the UNION of the ranks' chains (the chain moments are all-reduced;
+ * the reference reduces only the mean, utils/stats.jl:52-77, quirk Q15): every rank gets the same six numbers. */
 int nq_stat_analysis(nq_ctx_t ctx, const void* vals, int64_t B, int64_t L, nq_dtype vdtype, double out[6]);
 
 /* out[i] = |vals[i]|^2 (real of the same precision).  ref: BatchedGradSampler.jl:99 (abs2.(local_vals)) */
@@ -263,6 +265,10 @@ int nq_comm_destroy(nq_ctx_t ctx);
 int nq_comm_size(nq_ctx_t ctx, int* nranks, int* rank);   /* 1, 0 without a communicator */
 int nq_allreduce_sum(nq_ctx_t ctx, void* buf, int64_t n, nq_dtype dtype);   /* device buffer, in place */
 int nq_allreduce_mean(nq_ctx_t ctx, void* buf, int64_t n, nq_dtype dtype);
+/* Global sample count of the iteration when ranks own DIFFERENT numbers of samples (chains do not divide by the number
+ * of ranks): nq_center / nq_force_* normalise by it.  0 (default) = Ns * nranks.  The reference shards the chain
+ * length with ceil (Metropolis.jl:75) and divides by the worker count (mpi.jl:21-34). */
+int nq_comm_set_global_samples(nq_ctx_t ctx, int64_t ns_total);
 
 #ifdef __cplusplus
 }

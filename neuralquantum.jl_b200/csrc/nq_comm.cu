@@ -92,6 +92,12 @@ extern "C" int nq_comm_size(nq_ctx_t ctx, int* nranks, int* rank) {
     return NQ_OK;
 }
 
+extern "C" int nq_comm_set_global_samples(nq_ctx_t ctx, int64_t ns_total) {
+    if (!ctx || ns_total < 0) return NQ_ERR_ARG;
+    ctx->ns_total = ns_total;
+    return NQ_OK;
+}
+
 int nq_allreduce_device(nq_ctx_t ctx, void* buf, int64_t n, nq_dtype dtype, bool mean) {
     if (n <= 0) return NQ_OK;
     const bool dbl = nq_dtype_is_double(dtype);

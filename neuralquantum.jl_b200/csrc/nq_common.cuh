@@ -29,6 +29,7 @@ struct nq_ctx_s {
     // NCCL (nq_comm.cu)
     void* nccl_comm = nullptr;
     int nranks = 1, rank = 0;
+    int64_t ns_total = 0;          // global sample count override (nq_comm_set_global_samples), 0 = Ns * nranks
 };
 
 int nq_fail(nq_ctx_t ctx, int code, const char* fmt, ...);

@@ -1278,7 +1278,7 @@ extern "C" int nq_center(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, int64_t 
     }
     // a currently holds the (global) sum; divide by the global sample count
     {
-        int64_t ns_tot = Ns * ctx->nranks;
+        int64_t ns_tot = ctx->ns_total > 0 ? ctx->ns_total : Ns * ctx->nranks;
         cxd* tmp = (cxd*)nq_scratch(ctx, SL_W1, (size_t)P * sizeof(cxd));
         if (!tmp) return NQ_ERR_ALLOC;
         NQ_LAUNCH(ctx, colsum_final_kernel<double>, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)a, 1, P, 1.0 / (double)ns_tot, tmp);
@@ -1306,7 +1306,7 @@ extern "C" int nq_force_ket(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P
     void* dg = st.out(SL_OUT0, gradC, (size_t)P * nq_dtype_size(cdt));
     cxd* a = (cxd*)nq_scratch(ctx, SL_W0, (size_t)P * sizeof(cxd));
     if (!a || st.status != NQ_OK) return NQ_ERR_ALLOC;
-    int64_t ns_tot = Ns * ctx->nranks;
+    int64_t ns_tot = ctx->ns_total > 0 ? ctx->ns_total : Ns * ctx->nranks;
     NQ_CHECK(colsum_dispatch<true>(ctx, dtype, Oc, ldO, P, Ns, dE, 1.0 / (double)ns_tot, a));
     if (ctx->nccl_comm) NQ_CHECK(nq_allreduce_device(ctx, a, P, NQ_C128, false));   // C3
     NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)a, dg, P, (int)cdt, 0);
@@ -1330,7 +1330,7 @@ extern "C" int nq_force_liouvillian(nq_ctx_t ctx, const void* Lloc, const void* 
     cxd* avgd = (cxd*)nq_scratch(ctx, SL_W1, (size_t)P * sizeof(cxd));
     cxd* outd = (cxd*)nq_scratch(ctx, SL_W2, (size_t)P * sizeof(cxd));
     if (!a || !avgd || !outd) return NQ_ERR_ALLOC;
-    int64_t ns_tot = Ns * ctx->nranks;
+    int64_t ns_tot = ctx->ns_total > 0 ? ctx->ns_total : Ns * ctx->nranks;
     // (1/Ns) sum_s L_s conj(gL_ks), conjugated at the end: F_k = conj(.) - C avg_k
     NQ_CHECK(colsum_dispatch<true>(ctx, dtype, gLloc, ld, P, Ns, dL, 1.0 / (double)ns_tot, a));
     NQ_CUDA(ctx, cudaMemsetAsync(a + P, 0, sizeof(cxd), ctx->stream));
@@ -1610,18 +1610,35 @@ extern "C" int nq_stat_analysis(nq_ctx_t ctx, const void* vals, int64_t B, int64
     std::vector<double> h((size_t)B * 3);
     NQ_CUDA(ctx, cudaMemcpyAsync(h.data(), dst, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    // combine the per-chain moments exactly as utils/stats.jl:26-50 defines them
+    // combine the per-chain moments exactly as utils/stats.jl:26-50 defines them; under sharding over the union of
+    // the ranks' chains (two tiny all-reduces: counts and sums, then the spread around the global mean)
     double mr = 0, mi = 0, m2sum = 0;
     for (int64_t b = 0; b < B; b++) { mr += h[3 * b]; mi += h[3 * b + 1]; m2sum += h[3 * b + 2]; }
-    mr /= B; mi /= B;
+    double Bt = (double)B;
+    auto host_allreduce = [&](double* v, int n) -> int {
+        double* d = (double*)nq_scratch(ctx, SL_W1, 8 * sizeof(double));
+        if (!d) return NQ_ERR_ALLOC;
+        NQ_CUDA(ctx, cudaMemcpyAsync(d, v, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        NQ_CHECK(nq_allreduce_device(ctx, d, n, NQ_F64, false));
+        NQ_CUDA(ctx, cudaMemcpyAsync(v, d, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return NQ_OK;
+    };
+    if (ctx->nccl_comm) {
+        double v[4] = {Bt, mr, mi, m2sum};
+        NQ_CHECK(host_allreduce(v, 4));
+        Bt = v[0]; mr = v[1]; mi = v[2]; m2sum = v[3];
+    }
+    mr /= Bt; mi /= Bt;
     double between = 0;
     for (int64_t b = 0; b < B; b++) { double dr = h[3 * b] - mr, di = h[3 * b + 1] - mi; between += dr * dr + di * di; }
-    double var_chains_mean = L > 1 ? (m2sum / (double)(L - 1)) / (double)B : NAN;
-    double var_mu_ch = B > 1 ? between / (double)(B - 1) : NAN;
-    double var_mu = (B * L > 1) ? (m2sum + (double)L * between) / (double)(B * L - 1) : NAN;
+    if (ctx->nccl_comm) NQ_CHECK(host_allreduce(&between, 1));
+    double var_chains_mean = L > 1 ? (m2sum / (double)(L - 1)) / Bt : NAN;
+    double var_mu_ch = Bt > 1 ? between / (Bt - 1.0) : NAN;
+    double var_mu = (Bt * L > 1) ? (m2sum + (double)L * between) / (Bt * (double)L - 1.0) : NAN;
     double t = var_mu_ch / var_mu;
     out[0] = mr; out[1] = mi;
-    out[2] = sqrt(var_mu_ch / (double)B);
+    out[2] = sqrt(var_mu_ch / Bt);
     out[3] = var_chains_mean;
     out[4] = std::max(0.0, 0.5 * (t * (double)L - 1.0));
     out[5] = sqrt((double)(L - 1) / (double)L + t);

@@ -13,6 +13,7 @@ from .algorithms import (SR, Descent, Nesterov, update_, local_scalar, local_gra
                          sr_cg, sr_minres)
 from .iterative import BatchedSampler, BatchedObsDMSampler
 from .parallel import shard_chains, init_comm, world_from_env
+from . import models
 
 
 def LocalOperator(hilb):

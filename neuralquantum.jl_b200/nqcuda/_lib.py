@@ -121,6 +121,7 @@ _PROTOS = {
     "nq_comm_size": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
     "nq_allreduce_sum": (_i32, [_vp, _vp, _i64, _i32]),
     "nq_allreduce_mean": (_i32, [_vp, _vp, _i64, _i32]),
+    "nq_comm_set_global_samples": (_i32, [_vp, _i64]),
 }
 for _name, (_res, _args) in _PROTOS.items():
     _f = getattr(lib, _name)          # AttributeError here = header/library mismatch: fail loudly

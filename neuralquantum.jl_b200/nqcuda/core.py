@@ -19,6 +19,15 @@ class Context:
         L.check(L.lib.nq_ctx_create(int(device), stream, C.byref(h)))
         self.h = h
         self.device = int(device)
+        self.stream = int(stream) if stream else 0
+
+    def torch_stream(self):
+        """The context's stream as a torch stream: the host mirror's few torch ops (buffer fills, F copy, Nesterov
+        velocity, ExactSampler table) run under it so that they are ordered with the library's kernels."""
+        import torch
+        if not self.stream:
+            return torch.cuda.default_stream(torch.device("cuda", self.device))
+        return torch.cuda.ExternalStream(self.stream, device=torch.device("cuda", self.device))
 
     def close(self):
         if getattr(self, "h", None):
@@ -52,6 +61,10 @@ class Context:
 
     def allreduce_sum(self, dev_ptr, n, dtype):
         L.check(L.lib.nq_allreduce_sum(self.h, dev_ptr, n, dtype), self.h)
+
+    def set_global_samples(self, ns_total):
+        """Global sample count nq_center / nq_force_* normalise by (0 = Ns * nranks)."""
+        L.check(L.lib.nq_comm_set_global_samples(self.h, int(ns_total)), self.h)
 
     def allreduce_mean(self, dev_ptr, n, dtype):
         L.check(L.lib.nq_allreduce_mean(self.h, dev_ptr, n, dtype), self.h)

@@ -7,6 +7,7 @@ ref: src/IterativeInterface/build_Batched.jl:1-14, Samplers/CostFun/BatchedValSa
 Differences kept on purpose: all L slices of the chain are filled (Q3), S is
 normalised by the global sample count under sharding (Q5), statistics are global (Q15).
 """
+import copy
 import ctypes as C
 
 import numpy as np
@@ -46,12 +47,22 @@ class BatchedSampler:
         self.op = problem.to_device(ctx)
         self.nranks, self.rank = ctx.comm_size()
         self.B = int(batch_sz)
+        dev = torch.device("cuda", ctx.device)
+        # chains of this rank inside the global batch: ranks may own different numbers of chains (shard_chains hands
+        # the remainder to the first ranks), so the offset and the global count come from one all-reduce of the counts
+        self.chain_offset, self.B_total = self.rank * self.B, self.B * self.nranks
+        if self.nranks > 1:
+            counts = torch.zeros(self.nranks, dtype=torch.float64, device=dev)
+            counts[self.rank] = self.B
+            torch.cuda.current_stream(dev).synchronize()
+            ctx.allreduce_sum(counts.data_ptr(), self.nranks, L.NQ_F64)
+            counts = [int(round(c)) for c in counts.cpu().tolist()]
+            self.chain_offset, self.B_total = sum(counts[:self.rank]), sum(counts)
         cache_type = ExactSamplerCache if isinstance(sampler, ExactSampler) else MetropolisSamplerCache
-        self.cache = cache_type(sampler, net, self.B, chain_offset=self.rank * self.B, num_workers=self.nranks)
+        self.cache = cache_type(sampler, net, self.B, chain_offset=self.chain_offset, num_workers=self.nranks)
         self.L = self.cache.loc_chain_length if chain_length is None else int(chain_length)
         self.Ns = self.B * self.L
-        self.Ns_total = self.Ns * self.nranks
-        dev = torch.device("cuda", ctx.device)
+        self.Ns_total = self.B_total * self.L
         W = L.lib.nq_states_words(net.N)
         P, Ns = net.P, self.Ns
         ot, ct = _tdtype(net.out_dtype), _tdtype(net.cdtype)
@@ -78,7 +89,8 @@ class BatchedSampler:
     def sample_states(self):
         """_sample_state!: re-randomise the chains, burn, fill the L slices."""
         if isinstance(self.cache, ExactSamplerCache):
-            self.cache.sample_into(self.L, self.prow, self.pcol)
+            with _torch().cuda.stream(self.ctx.torch_stream()):
+                self.cache.sample_into(self.L, self.prow, self.pcol)
             return
         self.cache.randomize()
         self.cache.sample(self.sampler.burn_length, self.L,
@@ -108,6 +120,7 @@ class BatchedSampler:
         net, ctx, Ns, P = self.net, self.ctx, self.Ns, self.net.P
         oc = L.nq_dtype(net.out_dtype)
         cc = L.nq_dtype(net.cdtype)
+        ctx.set_global_samples(self.Ns_total if self.nranks > 1 else 0)
         L.check(L.lib.nq_center(ctx.h, self.O.data_ptr(), P, P, Ns, oc, self.avg.data_ptr()), ctx.h)
         if self.is_liouvillian:
             cost = C.c_double()
@@ -124,12 +137,14 @@ class BatchedSampler:
                 ctx.allreduce_sum(self.S.data_ptr(), P * P, L.nq_dtype(self.sdtype))
         else:
             torch = _torch()
-            self.F.copy_(self.gradC.real if self.real_params else self.gradC)
+            with torch.cuda.stream(ctx.torch_stream()):
+                self.F.copy_(self.gradC.real if self.real_params else self.gradC)
 
     def _avg_complex(self):
         if self.avg.dtype == self.gradC.dtype:
             return self.avg.data_ptr()
-        self._avgc = self.avg.to(self.gradC.dtype)
+        with _torch().cuda.stream(self.ctx.torch_stream()):
+            self._avgc = self.avg.to(self.gradC.dtype)
         return self._avgc.data_ptr()
 
     def statistics(self):
@@ -147,7 +162,7 @@ class BatchedSampler:
             # the gradient sampler of a Liouvillian owns a diagonal-chain observables sampler (BatchedGradSampler.jl)
             if getattr(self, "_obs_dm", None) is None:
                 self._obs_dm = BatchedObsDMSampler(self.net, self.sampler, batch_sz=self.B, chain_length=self.L,
-                                                   chain_offset=self.rank * self.B)
+                                                   chain_offset=self.chain_offset)
             self._obs_dm.add_observable_(name, obs)
             return
         if not hasattr(self, "observables"):
@@ -206,10 +221,11 @@ class BatchedSampler:
     def update_(self, opt, dw=None):
         dw = self.dw if dw is None else dw
         net = self.net
-        delta, eta = opt.step(dw)               # Descent: (dw, eta); Nesterov: velocity update on the device tensor
-        if delta.dtype != _tdtype(net.dtype):
-            delta = delta.to(_tdtype(net.dtype))
-        delta = delta.contiguous()
+        with _torch().cuda.stream(self.ctx.torch_stream()):
+            delta, eta = opt.step(dw)           # Descent: (dw, eta); Nesterov: velocity update on the device tensor
+            if delta.dtype != _tdtype(net.dtype):
+                delta = delta.to(_tdtype(net.dtype))
+            delta = delta.contiguous()
         L.check(L.lib.nq_update(net.h, delta.data_ptr(), float(eta)), self.ctx.h)
 
 
@@ -226,7 +242,10 @@ class BatchedObsDMSampler:
             raise ValueError("BatchedObsDMSampler needs an NDM density matrix")
         self.net, self.sampler, self.ctx = net, sampler, net.ctx
         self.B = int(batch_sz)
-        self.cache = MetropolisSamplerCache(sampler, net, self.B, chain_offset=chain_offset)
+        # its own Philox key: with the main chain's seed both chains would consume identical (site, uniform) streams
+        obs_sampler = copy.copy(sampler)
+        obs_sampler.seed = (int(sampler.seed) ^ 0x6F62735F646D) % (1 << 63)          # "obs_dm"
+        self.cache = MetropolisSamplerCache(obs_sampler, net, self.B, chain_offset=chain_offset)
         self.cache.set_mode(True)
         self.L = self.cache.loc_chain_length if chain_length is None else int(chain_length)
         self.Ns = self.B * self.L

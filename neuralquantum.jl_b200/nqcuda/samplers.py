@@ -121,7 +121,7 @@ class ExactSamplerCache:
         self.size = self.D * self.D if net.doubled else self.D
         if self.size > self.MAX_TABLE:
             raise ValueError("ExactSampler: %d table entries (Closed N < 24, Open N < 12)" % self.size)
-        self.gen = torch.Generator(device="cuda")
+        self.gen = torch.Generator(device=torch.device("cuda", net.ctx.device))
         self.gen.manual_seed((sampler.seed + 0x9E3779B97F4A7C15 * (chain_offset + 1)) % (1 << 63))
         self.cdf = None
 

@@ -57,40 +57,17 @@ def rand_states(hilb_kind, N, B, seed):
     return np.asfortranarray(OMOD.random_states(ohilb(hilb_kind, N), B, seed))
 
 
-# ---- the same physical models written with the PRODUCT's operator algebra --------------------
+# ---- the same physical models written with the PRODUCT's operator algebra (nqcuda/models.py) ----
 def p_tfim_1d(nq, N, h=1.0, J=1.0):
-    hilb = nq.HomogeneousSpin(N)
-    H = nq.LocalOperator(hilb)
-    for i in range(1, N + 1):
-        H = H - h * nq.sigmax(hilb, i)
-        H = H + (J * nq.sigmaz(hilb, i)) * nq.sigmaz(hilb, i % N + 1)
-    return hilb, H
+    return nq.models.tfim_1d(N, h, J)
 
 
 def p_tfim_2d(nq, Lx, h=3.0, J=1.0):
-    N = Lx * Lx
-    hilb = nq.HomogeneousSpin(N)
-    H = nq.LocalOperator(hilb)
-    for i in range(1, N + 1):
-        H = H - h * nq.sigmax(hilb, i)
-    for y in range(Lx):
-        for x in range(Lx):
-            i = 1 + x + Lx * y
-            for j in (1 + (x + 1) % Lx + Lx * y, 1 + x + Lx * ((y + 1) % Lx)):
-                if i != j:
-                    H = H + (J * nq.sigmaz(hilb, i)) * nq.sigmaz(hilb, j)
-    return hilb, H
+    return nq.models.tfim_2d(Lx, h, J)
 
 
 def p_lindblad_ising_1d(nq, N, g=0.4, V=2.0, fock=True):
-    hilb = nq.HomogeneousFock(N, 2) if fock else nq.HomogeneousSpin(N)
-    H = nq.LocalOperator(hilb)
-    jumps = []
-    for i in range(1, N + 1):
-        H = H + (g / 2.0) * nq.sigmax(hilb, i)
-        H = H + ((V / 4.0) * nq.sigmaz(hilb, i)) * nq.sigmaz(hilb, i % N + 1)
-        jumps.append(nq.sigmam(hilb, i))
-    return hilb, H, jumps, nq.liouvillian(H, jumps)
+    return nq.models.lindblad_ising_1d(N, g, V, fock)
 
 
 def enumerate_tables(tb, bits_row, bits_col=None):
