@@ -56,7 +56,9 @@ typedef enum { NQ_SOFTPLUS = 0, NQ_LOGCOSH = 1 } nq_activation;          /* ref:
 typedef enum { NQ_F32 = 0, NQ_F64 = 1, NQ_C64 = 2, NQ_C128 = 3 } nq_dtype;
 typedef enum { NQ_SPIN = 0, NQ_FOCK = 1 } nq_hilbert;                    /* values -1/+1 | 0/1, local dim 2 */
 typedef enum { NQ_KET = 0, NQ_SUPER = 1 } nq_space;                      /* H on sigma | Liouvillian on (sigma,sigma') */
-typedef enum { NQ_SOLVE_CHOLESKY = 0, NQ_SOLVE_CG = 1, NQ_SOLVE_MINRES = 2 } nq_solver;   /* ref: SR/SR.jl sr_cholesky | sr_cg | sr_minres */
+/* ref: SR/SR.jl sr_cholesky | sr_cg | sr_minres | sr_qlp.  NQ_SOLVE_QLP_WARM = MINRES-QLP started from the dw passed in
+ * (the warm-started restarts of SRIterative.jl:133-150). */
+typedef enum { NQ_SOLVE_CHOLESKY = 0, NQ_SOLVE_CG = 1, NQ_SOLVE_MINRES = 2, NQ_SOLVE_QLP = 3, NQ_SOLVE_QLP_WARM = 4 } nq_solver;
 
 typedef struct nq_ctx_s* nq_ctx_t;
 typedef struct nq_machine_s* nq_machine_t;
@@ -235,15 +237,21 @@ int nq_sr_solve(nq_ctx_t ctx, void* S, const void* F, int64_t P, nq_dtype sdtype
 int nq_sr_solve_matfree(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total,
                         nq_dtype dtype, const void* F, int real_params, double eps, double tol,
                         int64_t maxiter, void* dw, int64_t* iters);
-/* The same with the solver chosen by the caller: NQ_SOLVE_CG or NQ_SOLVE_MINRES (Paige-Saunders MINRES on the
- * Hermitian operator, x0 = 0, stop when the recurrence residual <= tol ||F||).  NQ_SOLVE_MINRES is also accepted by
- * nq_sr_solve on an explicit S.  ref: the sr_minres branch of SRIterative.jl:101-125. */
+/* The same with the solver chosen by the caller: NQ_SOLVE_CG, NQ_SOLVE_MINRES (Paige-Saunders MINRES on the
+ * Hermitian operator, x0 = 0, stop when the recurrence residual <= tol ||F||) or NQ_SOLVE_QLP / NQ_SOLVE_QLP_WARM
+ * (MINRES-QLP with the reference's stopping rules: min(relres, relAres) <= tol, xnorm and Acond limits 1e7; the exit
+ * flag 1..9 is left in nq_ctx_last_info; NQ_ERR_NOT_CONVERGED only for flag 8, the iteration limit).  All of them are also
+ * accepted by nq_sr_solve on an explicit S.
+ * ref: SRIterative.jl:92-125, External/IterativeSolvers/minresqlp.jl (quirks Q19-Q22 in oracle/minresqlp.py). */
 int nq_sr_solve_matfree_algo(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total,
                              nq_dtype dtype, const void* F, int real_params, double eps, nq_solver algo, double tol,
                              int64_t maxiter, void* dw, int64_t* iters);
 /* w <- w - eta dw on the machine's device parameters.  dw has the machine dtype (real for NDM).
  * ref: Optimisers/rules.jl:11-17, apply.jl:25-73 */
 int nq_update(nq_machine_t m, const void* dw, double eta);
+/* sr_multiplicative regulariser: S <- S + lambda Diagonal(diag(S)), in place on the device or host S (then solve with
+ * eps = 0).  ref: SRDirect.jl:66-72, SRIterative.jl:84-90 (lambda = max(lambda0 b^iter, lambda_min)). */
+int nq_sr_scale_diagonal(nq_ctx_t ctx, void* S, int64_t P, nq_dtype sdtype, double lambda);
 /* stat_analysis over [B chains, L] values (column-major [B,L]); out = {mean_re, mean_im, error,
  * variance, tau, R} host doubles.  vdtype: NQ_F32/F64/C64/C128.  ref: utils/stats.jl:26-50.
  * With a communicator the statistics are those of the UNION of the ranks' chains (the chain moments are all-reduced;

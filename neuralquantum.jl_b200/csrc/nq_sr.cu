@@ -26,48 +26,69 @@ namespace {
 // (coalesced), gridDim.y slices the samples; partials are summed in a fixed order.
 //   out[k] = scale * sum_s w[s] * (CONJ ? conj(X[k,s]) : X[k,s])        (w == nullptr: w = 1)
 // ======================================================================================
+// Compensated (double-double) accumulation: the force vector is a difference of O(1) averages that cancels to a few
+// per cent of their size, and the parity bound is element-wise 1e-11 (FP64 mode) -- plain sequential sums over 10^4-10^5
+// samples sit right at that bound.  TwoSum / TwoProduct (Knuth, Dekker with FMA) make the sums exact to ~1e-30 relative
+// to sum |terms| at no cost in time (the pass is bound by reading X once).
+struct dd { double hi, lo; };
+__device__ __forceinline__ void dd_add(dd& a, double p) {          // a += p, error-free
+    const double t = a.hi + p, bp = t - a.hi;
+    a.lo += (a.hi - (t - bp)) + (p - bp);
+    a.hi = t;
+}
+__device__ __forceinline__ void dd_fma(dd& a, double x, double y) { // a += x * y, error-free
+    const double p = x * y;
+    a.lo += fma(x, y, -p);
+    dd_add(a, p);
+}
+
 template <typename E, bool CONJ>
 __global__ void colsum_partial_kernel(const E* __restrict__ X, int64_t ld, int64_t P, int64_t Ns,
                                       const cx<typename elem_traits<E>::real>* __restrict__ w,
-                                      cxd* __restrict__ partial) {
+                                      cxd* __restrict__ partial, cxd* __restrict__ partial_lo) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= P) return;
     int64_t per = (Ns + gridDim.y - 1) / gridDim.y;
     int64_t s0 = blockIdx.y * per, s1 = s0 + per < Ns ? s0 + per : Ns;
-    double ar = 0.0, ai = 0.0;
+    dd ar = {0.0, 0.0}, ai = {0.0, 0.0};
     for (int64_t s = s0; s < s1; s++) {
         E x = X[k + ld * s];
         double xr = (double)real_part(x), xi = (double)imag_part(x);
         if (CONJ) xi = -xi;
         if (w) {
             double wr = (double)w[s].re, wi = (double)w[s].im;
-            ar += wr * xr - wi * xi;
-            ai += wr * xi + wi * xr;
-        } else { ar += xr; ai += xi; }
+            dd_fma(ar, wr, xr); dd_fma(ar, -wi, xi);
+            dd_fma(ai, wr, xi); dd_fma(ai, wi, xr);
+        } else { dd_add(ar, xr); dd_add(ai, xi); }
     }
-    partial[blockIdx.y * P + k] = cxd(ar, ai);
+    partial[blockIdx.y * P + k] = cxd(ar.hi, ai.hi);
+    partial_lo[blockIdx.y * P + k] = cxd(ar.lo, ai.lo);
 }
 
-template <typename E>   // out of E-compatible complex/real type, fixed-order reduction of the slices
-__global__ void colsum_final_kernel(const cxd* __restrict__ partial, int nslice, int64_t P, double scale,
-                                    cxd* __restrict__ out) {
+template <typename E>   // out of E-compatible complex/real type, fixed-order compensated reduction of the slices
+__global__ void colsum_final_kernel(const cxd* __restrict__ partial, const cxd* __restrict__ partial_lo, int nslice, int64_t P,
+                                    double scale, cxd* __restrict__ out) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= P) return;
-    double ar = 0.0, ai = 0.0;
-    for (int i = 0; i < nslice; i++) { ar += partial[i * P + k].re; ai += partial[i * P + k].im; }
-    out[k] = cxd(ar * scale, ai * scale);
+    dd ar = {0.0, 0.0}, ai = {0.0, 0.0};
+    for (int i = 0; i < nslice; i++) {
+        dd_add(ar, partial[i * P + k].re); dd_add(ai, partial[i * P + k].im);
+        if (partial_lo) { ar.lo += partial_lo[i * P + k].re; ai.lo += partial_lo[i * P + k].im; }
+    }
+    out[k] = cxd((ar.hi + ar.lo) * scale, (ai.hi + ai.lo) * scale);
 }
 
 template <typename E, bool CONJ>
 int colsum(nq_ctx_t ctx, const void* X, int64_t ld, int64_t P, int64_t Ns, const void* w, double scale, cxd* out) {
     int nslice = (int)std::min<int64_t>(std::max<int64_t>(1, Ns / 256), 4 * (int64_t)ctx->num_sms * 8 / std::max<int64_t>(1, (P + 127) / 128));
     nslice = std::max(1, std::min(nslice, 1024));
-    cxd* partial = (cxd*)nq_scratch(ctx, SL_W5, (size_t)nslice * P * sizeof(cxd));
+    cxd* partial = (cxd*)nq_scratch(ctx, SL_W5, (size_t)2 * nslice * P * sizeof(cxd));
     if (!partial) return NQ_ERR_ALLOC;
+    cxd* partial_lo = partial + (size_t)nslice * P;
     dim3 grid((unsigned)((P + 127) / 128), (unsigned)nslice);
     NQ_LAUNCH(ctx, (colsum_partial_kernel<E, CONJ>), grid, 128, 0, (const E*)X, ld, P, Ns,
-              (const cx<typename elem_traits<E>::real>*)w, partial);
-    NQ_LAUNCH(ctx, colsum_final_kernel<E>, (unsigned)((P + 255) / 256), 256, 0, partial, nslice, P, scale, out);
+              (const cx<typename elem_traits<E>::real>*)w, partial, partial_lo);
+    NQ_LAUNCH(ctx, colsum_final_kernel<E>, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)partial, (const cxd*)partial_lo, nslice, P, scale, out);
     return NQ_OK;
 }
 
@@ -932,13 +953,395 @@ __global__ void __launch_bounds__(256) chol_trsv_step_kernel(const E* __restrict
 }
 
 template <typename E>
+__global__ void scale_diag_kernel(E* __restrict__ A, int64_t P, typename elem_traits<E>::real f) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < P) A[i + P * i] = rscale(f, A[i + P * i]);
+}
+
+template <typename E>
 __global__ void add_diag_kernel(E* __restrict__ A, int64_t P, double eps) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < P) A[i + P * i] += from_real<E, double>(eps);
 }
 
+// --------------------------------------------------------------------------------------
+// Fused Cholesky solve: ONE persistent cooperative launch for the whole factorisation and both triangular solves.
+// Per block column (NB = 32):
+//   [panel]  the CTAs that own rows below the block (and CTA 0) factor the diagonal block in one warp (left-looking
+//            loop over shared memory: the fully unrolled register version is 64 KB of straight-line code that ran at
+//            instruction-fetch speed, 24 us per block), solve the block of the right-hand side with it -- the forward
+//            substitution rides on the panel, b is one more row of A -- and their threads apply the TRSM to their rows
+//            (right-looking in registers: 31 independent FMAs per step instead of a 496-long dependent chain);
+//   grid barrier;
+//   [update] the 32x32 blocks of the trailing matrix are dealt to WARPS: DMMA fragments straight from L2, no shared
+//            memory staging, no CTA barrier;
+//   grid barrier.
+// Backward solve L^H x = y: per block a barrier, the 32-step triangular solve (redundant per CTA) and one fused
+// multiply-add pass of every thread over its own entry of y.  Loads of data produced by other CTAs go through L2.
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ double ldcg_e(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ cxd ldcg_e(const cxd* p) { const double2 v = __ldcg(reinterpret_cast<const double2*>(p)); return cxd(v.x, v.y); }
+
+__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += nblocks;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// 1/sqrt(d) on the serial pivot chain: MUFU.RSQ64H seed + two Newton steps (the library rsqrt is ~3x longer)
+__device__ __forceinline__ double fast_rsqrt(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double hd = 0.5 * d;
+    double e = fma(-hd * y, y, 0.5);        // (1 - d y^2) / 2
+    y = fma(y, e, y);
+    e = fma(-hd * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hd * y, y, 0.5);
+    return fma(y, e, y);
+}
+
+// left-looking Cholesky of the block in shared memory, one warp, lane = row
+template <typename E>
+__device__ void potf2_warp_ll(E (*Lb)[NB + 1], double* Dinv, int nb, int64_t j0, int* info) {
+    const int r = threadIdx.x & 31;
+    for (int c = 0; c < nb; c++) {
+        E a0 = make_zero<E>(), a1 = make_zero<E>();
+        int k = 0;
+        for (; k + 1 < c; k += 2) { a0 += mulc(Lb[r][k], Lb[c][k]); a1 += mulc(Lb[r][k + 1], Lb[c][k + 1]); }
+        if (k < c) a0 += mulc(Lb[r][k], Lb[c][k]);
+        const E sv = Lb[r][c] - (a0 + a1);
+        double d = __shfl_sync(0xffffffffu, real_part(sv), c);
+        if (!(d > 0.0)) { if (r == 0) atomicCAS(info, -1, (int)(j0 + c)); d = 1.0; }
+        const double inv = (d > 1e-280 && d < 1e280) ? fast_rsqrt(d) : rsqrt(d);
+        if (r == c) { Lb[c][c] = from_real<E, double>(d * inv); Dinv[c] = inv; }
+        else if (r > c && r < nb) Lb[r][c] = rscale(inv, sv);
+        __syncwarp();
+    }
+}
+
+template <typename E>
+__global__ void __launch_bounds__(256) chol_fused_kernel(E* __restrict__ A, int64_t P, E* __restrict__ x,
+                                                         int* __restrict__ info, unsigned* __restrict__ bar,
+                                                         unsigned long long* __restrict__ prof) {
+    constexpr bool CPLX = sizeof(E) == 16;
+    constexpr int NPL = CPLX ? 2 : 1;
+    constexpr int KU = CPLX ? 2 : 8;           // k-steps of 4 whose fragments are in flight together
+    unsigned long long t_prev = 0, t_acc[6] = {0, 0, 0, 0, 0, 0};
+    auto tick = [&](int slot) {
+        if (prof && blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (slot >= 0) t_acc[slot] += t - t_prev;
+            t_prev = t;
+        }
+    };
+    tick(-1);
+    __shared__ E Lb[NB + 1][NB + 1];           // row NB: the block of the right-hand side (factor_block)
+    __shared__ double Dinv[NB];
+    __shared__ double dsv[NB];
+    __shared__ E yb[NB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned nblocks = gridDim.x;
+    unsigned target = 0;
+    const int64_t nblk = (P + NB - 1) / NB;
+    const int g = lane >> 2, tq = lane & 3;
+    const double* Ad = reinterpret_cast<const double*>(A);
+    double* Aw = reinterpret_cast<double*>(A);
+    // factor the diagonal block at j0 (already updated, in Lb) and solve its block of the right-hand side, CTA 0, all 256
+    // threads: right-looking elimination in shared memory on the UNSCALED columns (A[r][c2] -= A[r][c] conj(A[c2][c]) / d_c,
+    // one barrier per column, the pivot reciprocal is recomputed by every thread), the right-hand side rides along as
+    // row NB (it holds conj(y) l_cc: the last row of the factor of the bordered matrix).  Results go straight to A and
+    // x -- the other CTAs only read them after the next grid barrier.
+    auto factor_block = [&](int64_t j0, int nb) {
+        if (tid < NB) Lb[NB][tid] = tid < nb ? conj(ldcg_e(x + j0 + tid)) : make_zero<E>();
+        int er[5], ec[5];
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            const int e = tid + 256 * q;
+            er[q] = e / NB; ec[q] = e % NB;
+            const bool ok = e < (NB + 1) * NB && ec[q] < nb && ((er[q] >= ec[q] && er[q] < nb) || er[q] == NB);
+            if (!ok) ec[q] = -1;
+        }
+        __syncthreads();
+        for (int c = 0; c < nb; c++) {
+            double d = real_part(Lb[c][c]);
+            if (!(d > 0.0)) { if (tid == 0) atomicCAS(info, -1, (int)(j0 + c)); d = 1.0; }
+            if (tid == 0) dsv[c] = d;
+            const double rd = 1.0 / d;
+#pragma unroll
+            for (int q = 0; q < 5; q++)
+                if (ec[q] > c) Lb[er[q]][ec[q]] -= rscale(rd, mulc(Lb[er[q]][c], Lb[ec[q]][c]));
+            __syncthreads();
+        }
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            const int r = er[q], c = ec[q];
+            if (c < 0) continue;
+            const double dd = dsv[c];
+            const double inv = (dd > 1e-280 && dd < 1e280) ? fast_rsqrt(dd) : rsqrt(dd);
+            if (r == NB) x[j0 + c] = conj(rscale(inv, Lb[NB][c]));
+            else A[(j0 + r) + P * (j0 + c)] = r == c ? from_real<E, double>(dd * inv) : rscale(inv, Lb[r][c]);
+        }
+        // the strict upper triangle of the block is not referenced by the solves (the legacy path zeroes it)
+        __syncthreads();
+    };
+    if (blockIdx.x == 0) {
+        const int nb0 = (int)(P < NB ? P : NB);
+        for (int i = tid; i < NB * NB; i += 256) {
+            const int r = i % NB, c = i / NB;
+            Lb[r][c] = (r < nb0 && c < nb0 && c <= r) ? A[r + P * c] : make_zero<E>();
+        }
+        factor_block(0, nb0);
+    }
+    grid_sync(bar, target, nblocks);
+    for (int64_t kb = 0; kb < nblk; kb++) {
+        const int64_t j0 = kb * NB;
+        const int nb = (int)((P - j0) < NB ? (P - j0) : NB);
+        const int64_t base = j0 + nb, below = P - base;
+        if (below <= 0) break;
+        // ---- panel: the CTAs that own rows below the block load the factored block and y_blk, then TRSM their rows
+        const bool has_rows = (int64_t)blockIdx.x * 256 < below;
+        if (has_rows) {
+            for (int i = tid; i < NB * NB; i += 256) {
+                const int r = i % NB, c = i / NB;
+                Lb[r][c] = (r < nb && c < nb && c <= r) ? ldcg_e(A + (j0 + r) + P * (j0 + c)) : make_zero<E>();
+            }
+            if (tid < NB) yb[tid] = tid < nb ? ldcg_e(x + j0 + tid) : make_zero<E>();
+            __syncthreads();
+            if (tid < NB) Dinv[tid] = tid < nb ? 1.0 / real_part(Lb[tid][tid]) : 1.0;
+            __syncthreads();
+            tick(0);
+            const int64_t row = base + (int64_t)blockIdx.x * 256 + tid;
+            if (row < P) {
+                E xr[NB];
+#pragma unroll
+                for (int c = 0; c < NB; c++) xr[c] = c < nb ? ldcg_e(A + row + P * (j0 + c)) : make_zero<E>();
+                E bacc = ldcg_e(x + row);
+#pragma unroll
+                for (int c = 0; c < NB; c++) {
+                    if (c < nb) {
+                        const E xc = rscale(Dinv[c], xr[c]);
+                        xr[c] = xc;
+#pragma unroll
+                        for (int c2 = c + 1; c2 < NB; c2++) xr[c2] -= mulc(xc, Lb[c2][c]);
+                        bacc -= xc * yb[c];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NB; c++) if (c < nb) A[row + P * (j0 + c)] = xr[c];
+                x[row] = bacc;
+            }
+            __syncthreads();
+        }
+        tick(1);
+        grid_sync(bar, target, nblocks);
+        tick(2);
+        // ---- look-ahead on CTA 0: update the NEXT diagonal block with this panel, factor it and solve its block of b
+        //      while the other CTAs run the trailing update (they skip item 0)
+        if (blockIdx.x == 0) {
+            const int nbn = (int)((P - base) < NB ? (P - base) : NB);
+            __shared__ E Xn[NB][NB + 1];
+            for (int i = tid; i < NB * NB; i += 256) {
+                const int r = i % NB, c = i / NB;
+                const bool ok = r < nbn && c < nb;
+                Xn[r][c] = ok ? ldcg_e(A + (base + r) + P * (j0 + c)) : make_zero<E>();
+            }
+            __syncthreads();
+            for (int i = tid; i < NB * NB; i += 256) {
+                const int r = i % NB, c = i / NB;
+                E v = make_zero<E>();
+                if (r < nbn && c <= r) {
+                    v = ldcg_e(A + (base + r) + P * (base + c));
+                    for (int q = 0; q < NB; q++) v -= mulc(Xn[r][q], Xn[c][q]);
+                }
+                Lb[r][c] = v;
+            }
+            factor_block(base, nbn);
+        }
+        // ---- trailing update: 32x32 blocks dealt to warps, fragments straight from L2 (nb == NB here)
+        if (blockIdx.x != 0 || nblocks == 1) {
+            const int64_t n32 = (below + 31) / 32;
+            const int64_t nitems = n32 * (n32 + 1) / 2;
+            const int64_t wid = nblocks == 1 ? warp : (int64_t)(blockIdx.x - 1) * 8 + warp;
+            const int64_t wstride = nblocks == 1 ? 8 : (int64_t)(nblocks - 1) * 8;
+            for (int64_t t = 1 + wid; t < nitems; t += wstride) {
+                int bi = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+                while ((int64_t)(bi + 1) * (bi + 2) / 2 <= t) bi++;
+                while ((int64_t)bi * (bi + 1) / 2 > t) bi--;
+                const int bj = (int)(t - (int64_t)bi * (bi + 1) / 2);
+                const int64_t i0 = base + (int64_t)bi * 32, l0 = base + (int64_t)bj * 32;
+                double cre[4][4][2], cim[CPLX ? 4 : 1][CPLX ? 4 : 1][2];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        cre[i][j][0] = cre[i][j][1] = 0.0;
+                        if (CPLX) cim[i][j][0] = cim[i][j][1] = 0.0;
+                    }
+#pragma unroll 1
+                for (int k0 = 0; k0 < NB / 4; k0 += KU) {
+                    double ar[KU][4], ai[CPLX ? KU : 1][4], br[KU][4], bi_[CPLX ? KU : 1][4];
+#pragma unroll
+                    for (int u = 0; u < KU; u++) {
+                        const int64_t colo = P * (j0 + 4 * (k0 + u) + tq);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int64_t ra = i0 + 8 * i + g, rb = l0 + 8 * i + g;
+                            if (CPLX) {
+                                const double2 va = ra < P ? __ldcg(reinterpret_cast<const double2*>(Ad) + ra + colo) : make_double2(0.0, 0.0);
+                                const double2 vb = rb < P ? __ldcg(reinterpret_cast<const double2*>(Ad) + rb + colo) : make_double2(0.0, 0.0);
+                                ar[u][i] = va.x; ai[u][i] = va.y; br[u][i] = vb.x; bi_[u][i] = vb.y;
+                            } else {
+                                ar[u][i] = ra < P ? __ldcg(Ad + ra + colo) : 0.0;
+                                br[u][i] = rb < P ? __ldcg(Ad + rb + colo) : 0.0;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < KU; u++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                dmma(cre[i][j][0], cre[i][j][1], ar[u][i], br[u][j]);
+                                if (CPLX) {
+                                    dmma(cre[i][j][0], cre[i][j][1], ai[u][i], bi_[u][j]);
+                                    dmma(cim[i][j][0], cim[i][j][1], ai[u][i], br[u][j]);
+                                    dmma(cim[i][j][0], cim[i][j][1], ar[u][i], -bi_[u][j]);
+                                }
+                            }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int64_t row = i0 + i * 8 + g, col = l0 + j * 8 + 2 * tq + h;
+                            if (row < P && col < P && row >= col) {
+                                const int64_t at = (row + P * col) * NPL;
+                                Aw[at] = __ldcg(Ad + at) - cre[i][j][h];
+                                if (CPLX) Aw[at + 1] = __ldcg(Ad + at + 1) - cim[i][j][h];
+                            }
+                        }
+            }
+        }
+        __syncthreads();
+        tick(3);
+        grid_sync(bar, target, nblocks);
+        tick(4);
+    }
+    // ---- backward solve L^H x = y: only the CTAs that own entries of y take part (their own barrier counter).
+    // Thread k owns y[k] in a REGISTER for the whole phase (only it updates that entry); per block: the owners of the
+    // block's entries publish them, barrier, every CTA solves the 32x32 triangular system redundantly (the diagonal block
+    // and this thread's 32 entries of L for the step were prefetched before the barrier: they are final since the
+    // factorisation), one fused multiply-add pass over the registers.
+    const unsigned nb2 = (unsigned)((P + 255) / 256) < nblocks ? (unsigned)((P + 255) / 256) : nblocks;
+    if (blockIdx.x >= nb2) return;
+    unsigned* bar2 = bar + 1;
+    unsigned target2 = 0;
+    const int64_t myk = (int64_t)blockIdx.x * 256 + tid;            // nb2 * 256 >= P: one entry per thread
+    E myy = myk < P ? ldcg_e(x + myk) : make_zero<E>();
+    // software pipeline: the (static) diagonal block and column segment of block bi - 1 are fetched while block bi is solved
+    E dnext[4], lseg[NB], lnext[NB];
+    auto fetch = [&](int64_t bi, E* dblk, E* seg) {
+        const int64_t j0 = bi * NB;
+        const int nb = (int)((P - j0) < NB ? (P - j0) : NB);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = tid + 256 * q, r = i % NB, c = i / NB;
+            dblk[q] = (r < nb && c < nb) ? ldcg_e(A + (j0 + r) + P * (j0 + c)) : make_zero<E>();
+        }
+        if (myk < j0) {
+            const E* col = A + j0 + P * myk;
+#pragma unroll
+            for (int r = 0; r < NB; r++) seg[r] = r < nb ? ldcg_e(col + r) : make_zero<E>();
+        }
+    };
+    fetch(nblk - 1, dnext, lnext);
+    for (int64_t bi = nblk - 1; bi >= 0; bi--) {
+        const int64_t j0 = bi * NB;
+        const int nb = (int)((P - j0) < NB ? (P - j0) : NB);
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int i = tid + 256 * q; Lb[i % NB][i / NB] = dnext[q]; }
+#pragma unroll
+        for (int r = 0; r < NB; r++) lseg[r] = lnext[r];
+        if (myk >= j0 && myk < j0 + nb) x[myk] = myy;                // publish y_blk (final value of these entries)
+        if (bi > 0) fetch(bi - 1, dnext, lnext);
+        grid_sync(bar2, target2, nb2);
+        if (warp == 0) {
+            E v = lane < nb ? ldcg_e(x + j0 + lane) : make_zero<E>();
+            const double dinv = lane < nb ? 1.0 / real_part(Lb[lane][lane]) : 1.0;
+            for (int c = nb - 1; c >= 0; c--) {
+                const E xc = rscale(__shfl_sync(0xffffffffu, dinv, c), lane_bcast(v, c));
+                if (lane == c) v = xc;
+                if (lane < c) v -= mulc(xc, Lb[c][lane]);   // conj(L[c][lane]) x_c
+            }
+            yb[lane] = lane < nb ? v : make_zero<E>();
+        }
+        __syncthreads();
+        if (myk < j0) {
+            E a0 = make_zero<E>(), a1 = make_zero<E>();
+#pragma unroll
+            for (int r = 0; r < NB; r += 2) { a0 += mulc(yb[r], lseg[r]); a1 += mulc(yb[r + 1], lseg[r + 1]); }
+            myy -= a0 + a1;
+        } else if (myk < j0 + nb) {
+            myy = yb[myk - j0];                                      // x of the block: final
+        }
+        __syncthreads();                                             // yb / Lb are reused by the next block
+    }
+    if (myk < P) x[myk] = myy;
+    tick(5);
+    if (prof && blockIdx.x == 0 && tid == 0) for (int i = 0; i < 6; i++) prof[i] = t_acc[i];
+}
+
+template <typename E>
+int cholesky_solve_fused(nq_ctx_t ctx, E* A, int64_t P, E* x, int* dinfo, bool* used) {
+    *used = false;
+    int coop = 0;
+    NQ_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+    if (!coop) return NQ_OK;
+    auto kern = chol_fused_kernel<E>;
+    int per_sm = 0;
+    NQ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+    if (per_sm < 1) return NQ_OK;
+    // enough warps for the first trailing update, never more CTAs than are co-resident
+    const int64_t n32 = (P + 31) / 32;
+    int grid = (int)std::min<int64_t>((int64_t)ctx->num_sms, std::max<int64_t>(1, (n32 * (n32 + 1) / 2 + 7) / 8));
+    unsigned* bar = (unsigned*)((char*)dinfo + 8);
+    NQ_CUDA(ctx, cudaMemsetAsync(bar, 0, 8, ctx->stream));
+    static const bool want_prof = getenv("NQ_CHOL_PROF") != nullptr;
+    unsigned long long* prof = want_prof ? (unsigned long long*)((char*)dinfo + 16) : nullptr;
+    void* args[] = {(void*)&A, (void*)&P, (void*)&x, (void*)&dinfo, (void*)&bar, (void*)&prof};
+    NQ_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(256), args, 0, ctx->stream));
+    ctx->launches++;
+    if (want_prof) {
+        unsigned long long h[6];
+        NQ_CUDA(ctx, cudaMemcpyAsync(h, prof, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        fprintf(stderr, "chol_fused P=%lld grid=%d us: potf2 %.1f trsm %.1f bar1 %.1f update %.1f bar2 %.1f backward %.1f\n",
+                (long long)P, grid, h[0] * 1e-3, h[1] * 1e-3, h[2] * 1e-3, h[3] * 1e-3, h[4] * 1e-3, h[5] * 1e-3);
+    }
+    *used = true;
+    return NQ_OK;
+}
+
 template <typename E>
 int cholesky_solve(nq_ctx_t ctx, E* A, int64_t P, E* x, int* dinfo) {
+    static const bool legacy = [] { const char* e = getenv("NQ_CHOL"); return e && !strcmp(e, "legacy"); }();
+    if (!legacy) {
+        bool used = false;
+        NQ_CHECK(cholesky_solve_fused<E>(ctx, A, P, x, dinfo, &used));
+        if (used) return NQ_OK;
+    }
     for (int64_t j0 = 0; j0 < P; j0 += NB) {
         int nb = (int)std::min<int64_t>(NB, P - j0);
         int64_t below = P - j0 - nb;
@@ -1214,6 +1617,187 @@ int minres_solve(CgOps<E>& ops, const E* b, double tol, int64_t maxiter, E* x, i
     return (phibar <= tol * beta1 || beta == 0.0) ? NQ_OK : NQ_ERR_NOT_CONVERGED;
 }
 
+// --------------------------------------------------------------------------------------
+// MINRES-QLP as the reference runs it (External/IterativeSolvers/minresqlp.jl; restated with its quirks Q19-Q22 in
+// oracle/minresqlp.py): Lanczos + left Givens rotations like MINRES, plus right rotations that keep the solution the
+// minimum-length one on singular systems.  The reference's MINRES/QLP switch never takes the MINRES branch (Q19), so
+// every iteration is a QLP update.  Scalars live on the host (two dot products per iteration come back), vectors on
+// the device; x0 != nullptr: warm start (iterate on F - A x0, add x0 at the end) for the restart ladder.
+// flag: 1 relres <= tol, 2 relAres <= tol, 3/4 machine-precision variants, 5 eigenvector, 6 xnorm limit, 7 Acond limit,
+// 8 iteration limit, 9 singular last rotation.
+// --------------------------------------------------------------------------------------
+template <typename E>
+__global__ void qlp_update_kernel(int mode, const E* __restrict__ v, E* __restrict__ w, E* __restrict__ wl, E* __restrict__ wl2,
+                                  E* __restrict__ xl2, E* __restrict__ x, double cr1, double sr1, double cr2, double sr2,
+                                  double ul2, double ul, double u, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const E vi = v[i], wi = w[i], wli = wl[i];
+    E nwl2, nwl, nw;
+    if (mode == 1) { nwl2 = wli; nwl = rscale(sr1, vi); nw = rscale(-cr1, vi); }
+    else if (mode == 2) { nwl2 = wli; nwl = rscale(cr1, wi) + rscale(sr1, vi); nw = rscale(sr1, wi) - rscale(cr1, vi); }
+    else {
+        const E t2 = wli, t1 = wi;
+        const E wp = rscale(sr2, t2) - rscale(cr2, vi);
+        nwl2 = rscale(cr2, t2) + rscale(sr2, vi);
+        nwl = rscale(cr1, t1) + rscale(sr1, wp);
+        nw = rscale(sr1, t1) - rscale(cr1, wp);
+    }
+    const E nxl2 = xl2[i] + rscale(ul2, nwl2);
+    wl2[i] = nwl2; wl[i] = nwl; w[i] = nw; xl2[i] = nxl2;
+    x[i] = nxl2 + rscale(ul, nwl) + rscale(u, nw);
+}
+
+static void sym_givens(double a, double b, double& c, double& s, double& r) {
+    auto sgn = [](double t) { return (double)((t > 0.0) - (t < 0.0)); };
+    if (b == 0.0) { c = a == 0.0 ? 1.0 : sgn(a); s = 0.0; r = fabs(a); }
+    else if (a == 0.0) { c = 0.0; s = sgn(b); r = fabs(b); }
+    else if (fabs(b) > fabs(a)) { const double t = a / b; s = sgn(b) / sqrt(1.0 + t * t); c = s * t; r = b / s; }
+    else { const double t = b / a; c = sgn(a) / sqrt(1.0 + t * t); s = c * t; r = a / c; }
+}
+
+template <typename E>
+int qlp_solve(CgOps<E>& ops, const E* b, const E* x0, double tol, int64_t maxiter, E* x, int64_t* iters, int* flag_out) {
+    nq_ctx_t ctx = ops.ctx;
+    const int64_t P = ops.P;
+    E* work = (E*)nq_scratch(ctx, SL_W2, (size_t)9 * P * sizeof(E) + 64);
+    double* dsc = (double*)nq_scratch(ctx, SL_W1, 128);
+    if (!work || !dsc) return NQ_ERR_ALLOC;
+    E *ra = work, *rb = work + P, *rc = work + 2 * P, *v = work + 3 * P, *w = work + 4 * P, *wl = work + 5 * P,
+      *wl2 = work + 6 * P, *xl2 = work + 7 * P, *xs = work + 8 * P;
+    const unsigned gv = (unsigned)((P + 255) / 256);
+    NQ_CUDA(ctx, cudaMemsetAsync(w, 0, (size_t)4 * P * sizeof(E), ctx->stream));          // w, wl, wl2, xl2
+    NQ_CUDA(ctx, cudaMemsetAsync(ra, 0, (size_t)P * sizeof(E), ctx->stream));             // r1 = 0
+    NQ_CUDA(ctx, cudaMemcpyAsync(rb, b, (size_t)P * sizeof(E), cudaMemcpyDeviceToDevice, ctx->stream));   // r2 = b
+    if (x0) {                                                                                               // r2 = b - A x0
+        NQ_CUDA(ctx, cudaMemcpyAsync(xs, x0, (size_t)P * sizeof(E), cudaMemcpyDeviceToDevice, ctx->stream));
+        NQ_CHECK(ops.matvec(xs, rc));
+        NQ_LAUNCH(ctx, axpy_real_kernel<E>, gv, 256, 0, rb, -1.0, (const E*)rc, P);
+    }
+    NQ_CUDA(ctx, cudaMemsetAsync(x, 0, (size_t)P * sizeof(E), ctx->stream));
+    double h[2];
+    auto dot = [&](const E* a_, const E* b_, double* out) -> int {
+        NQ_LAUNCH(ctx, dot_kernel<E>, 1, 1024, 0, a_, b_, P, dsc);
+        NQ_CUDA(ctx, cudaMemcpyAsync(h, dsc, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *out = h[0];
+        return NQ_OK;
+    };
+    double bb;
+    NQ_CHECK(dot(rb, rb, &bb));
+    const double beta1 = sqrt(bb);
+    int flag0 = -2, flag = flag0;
+    int64_t it = 0, qlp_it = 0;
+    if (beta1 == 0.0) {
+        if (x0) NQ_LAUNCH(ctx, axpy_real_kernel<E>, gv, 256, 0, x, 1.0, (const E*)xs, P);
+        if (iters) *iters = 0;
+        if (flag_out) *flag_out = 0;
+        return NQ_OK;
+    }
+    const double TranCond = 10e6, maxxnorm = 10e6, Acondlim = TranCond;      // minresqlp.jl:98-100, :150 (Q21)
+    const double realmin = 2.2250738585072014e-308, dbl_eps = 2.220446049250313e-16;
+    E *r1 = ra, *r2 = rb, *r3 = rc;                 // r3 is the free buffer; the reference keeps r3 == r2 between iterations
+    double beta = 0.0, tau = 0.0, taul = 0.0, phi = beta1, betan = beta1, gmin = 0.0;
+    double cs = -1.0, sn = 0.0, cr1 = -1.0, sr1 = 0.0, cr2 = -1.0, sr2 = 0.0;
+    double dltan = 0.0, eplnn = 0.0, gama = 0.0, gamal = 0.0, gamal2 = 0.0;
+    double eta = 0.0, etal = 0.0, etal2 = 0.0, vepln = 0.0, veplnl = 0.0, veplnl2 = 0.0;
+    double ul3 = 0.0, ul2 = 0.0, ul = 0.0, u = 0.0;
+    double rnorm = beta1, xnorm = 0.0, xl2norm = 0.0, Anorm = 0.0, Acond = 1.0;
+    double relres = beta1 / (beta1 + 1e-50), relAres = 0.0, resnorm = 123.0;
+    int64_t iteration = 1;
+    while (!(iteration > maxiter || resnorm <= tol || flag != flag0)) {
+        iteration++;
+        it++;
+        const double betal = beta;
+        beta = betan;
+        NQ_LAUNCH(ctx, scale_copy_kernel<E>, gv, 256, 0, v, (const E*)r2, 1.0 / beta, P);          // v = r3 / beta
+        NQ_CHECK(ops.matvec(v, r3));                                                               // r3 = A v (shift inside)
+        if (it > 1) NQ_LAUNCH(ctx, axpy_real_kernel<E>, gv, 256, 0, r3, -beta / betal, (const E*)r1, P);
+        double alfa;
+        NQ_CHECK(dot(v, r3, &alfa));                                                               // Re <v, r3>
+        NQ_LAUNCH(ctx, axpy_real_kernel<E>, gv, 256, 0, r3, -alfa / beta, (const E*)r2, P);
+        { E* t = r1; r1 = r2; r2 = r3; r3 = t; }
+        double b2;
+        NQ_CHECK(dot(r2, r2, &b2));
+        betan = sqrt(b2);
+        if (it == 1 && betan == 0.0) {
+            if (alfa == 0.0) flag = 0;
+            else { flag = -1; NQ_LAUNCH(ctx, scale_copy_kernel<E>, gv, 256, 0, x, b, 1.0 / alfa, P); }
+            break;
+        }
+        const double pnorm = sqrt(betal * betal + alfa * alfa + betan * betan);
+        const double dbar = dltan;
+        double dlta = cs * dbar + sn * alfa;
+        const double gbar = sn * dbar - cs * alfa;
+        eplnn = sn * betan;
+        dltan = -cs * betan;
+        gamal2 = gamal; gamal = gama;
+        sym_givens(gbar, betan, cs, sn, gama);
+        const double taul2 = taul;
+        taul = tau;
+        tau = cs * phi;
+        phi = sn * phi;
+        if (it > 2) {
+            veplnl2 = veplnl; etal2 = etal; etal = eta;
+            const double dlta_tmp = sr2 * vepln - cr2 * dlta;
+            veplnl = cr2 * vepln + sr2 * dlta;
+            dlta = dlta_tmp;
+            eta = sr2 * gama;
+            gama = -cr2 * gama;
+        }
+        if (it > 1) {
+            sym_givens(gamal, dlta, cr1, sr1, gamal);
+            vepln = sr1 * gama;
+            gama = -cr1 * gama;
+        }
+        const double ul4 = ul3;
+        ul3 = ul2;
+        if (it > 2) ul2 = (taul2 - etal2 * ul4 - veplnl2 * ul3) / gamal2;
+        if (it > 1) ul = (taul - etal * ul3 - veplnl * ul2) / gamal;
+        const double xnorm_tmp = sqrt(xl2norm * xl2norm + ul2 * ul2 + ul * ul);
+        if (fabs(gama) > realmin && xnorm_tmp < maxxnorm) {
+            u = (tau - eta * ul2 - vepln * ul) / gama;
+            if (sqrt(xnorm_tmp * xnorm_tmp + u * u) > maxxnorm) { u = 0.0; flag = 6; }
+        } else { u = 0.0; flag = 9; }
+        xl2norm = sqrt(xl2norm * xl2norm + ul2 * ul2);
+        xnorm = sqrt(xl2norm * xl2norm + ul * ul + u * u);
+        qlp_it++;
+        NQ_LAUNCH(ctx, qlp_update_kernel<E>, gv, 256, 0, it == 1 ? 1 : (it == 2 ? 2 : 3), (const E*)v, w, wl, wl2, xl2, x,
+                  cr1, sr1, cr2, sr2, ul2, ul, u, P);
+        sym_givens(gamal, eplnn, cr2, sr2, gamal);
+        const double abs_gama = fabs(gama);
+        Anorm = std::max(std::max(Anorm, pnorm), std::max(gamal, abs_gama));
+        if (it == 1) gmin = gama;                                                                  // never updated again (Q20)
+        const double Acondl = Acond, rnorml = rnorm, relresl = relres;
+        Acond = Anorm / gmin;
+        if (flag != 9) rnorm = phi;
+        relres = rnorm / (Anorm * xnorm + beta1);
+        const double rootl = sqrt(gbar * gbar + dltan * dltan);
+        relAres = rootl / Anorm;
+        const double epsx = Anorm * xnorm * dbl_eps;
+        if (flag == flag0 || flag == 9) {
+            const double t1 = 1.0 + relres, t2 = 1.0 + relAres;
+            if (it >= maxiter) flag = 8;
+            if (Acond >= Acondlim) flag = 7;
+            if (xnorm >= maxxnorm) flag = 6;
+            if (epsx >= beta1) flag = 5;
+            if (t2 <= 1.0) flag = 4;
+            if (t1 <= 1.0) flag = 3;
+            if (relAres <= tol) flag = 2;
+            if (relres <= tol) flag = 1;
+        }
+        if (flag == 2 || flag == 4 || flag == 6 || flag == 7) { it--; Acond = Acondl; rnorm = rnorml; relres = relresl; }
+        resnorm = std::min(relres, relAres);
+    }
+    if (x0) NQ_LAUNCH(ctx, axpy_real_kernel<E>, gv, 256, 0, x, 1.0, (const E*)xs, P);
+    if (iters) *iters = it;
+    if (flag_out) *flag_out = flag;
+    ctx->info = flag;
+    (void)qlp_it;
+    // the reference counts every exit as converged (Q22); the iteration limit is reported so that callers can tell
+    return flag == 8 ? NQ_ERR_NOT_CONVERGED : NQ_OK;
+}
+
 template <typename E>
 __global__ void update_kernel(E* __restrict__ w, const E* __restrict__ dw, typename elem_traits<E>::real eta, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -1281,7 +1865,7 @@ extern "C" int nq_center(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, int64_t 
         int64_t ns_tot = ctx->ns_total > 0 ? ctx->ns_total : Ns * ctx->nranks;
         cxd* tmp = (cxd*)nq_scratch(ctx, SL_W1, (size_t)P * sizeof(cxd));
         if (!tmp) return NQ_ERR_ALLOC;
-        NQ_LAUNCH(ctx, colsum_final_kernel<double>, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)a, 1, P, 1.0 / (double)ns_tot, tmp);
+        NQ_LAUNCH(ctx, colsum_final_kernel<double>, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)a, (const cxd*)nullptr, 1, P, 1.0 / (double)ns_tot, tmp);
         a = tmp;
     }
     dim3 grid((unsigned)((P + 127) / 128), (unsigned)std::min<int64_t>(Ns, 4096));
@@ -1435,6 +2019,31 @@ __global__ void cxd_to_real_kernel(const cxd* __restrict__ in, double* __restric
     if (i < n) out[i] = in[i].re;
 }
 
+extern "C" int nq_sr_scale_diagonal(nq_ctx_t ctx, void* S, int64_t P, nq_dtype sdtype, double lambda) {
+    if (!ctx || !S || P <= 0) return NQ_ERR_ARG;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t es = nq_dtype_size(sdtype);
+    const bool on_dev = nq_is_device_ptr(S);
+    void* d = S;
+    if (!on_dev) {
+        d = nq_scratch(ctx, SL_W0, (size_t)P * P * es);
+        if (!d) return NQ_ERR_ALLOC;
+        NQ_CUDA(ctx, cudaMemcpyAsync(d, S, (size_t)P * P * es, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const unsigned g = (unsigned)((P + 255) / 256);
+    switch (sdtype) {
+        case NQ_F32: NQ_LAUNCH(ctx, scale_diag_kernel<float>, g, 256, 0, (float*)d, P, (float)(1.0 + lambda)); break;
+        case NQ_F64: NQ_LAUNCH(ctx, scale_diag_kernel<double>, g, 256, 0, (double*)d, P, 1.0 + lambda); break;
+        case NQ_C64: NQ_LAUNCH(ctx, scale_diag_kernel<cxf>, g, 256, 0, (cxf*)d, P, (float)(1.0 + lambda)); break;
+        default: NQ_LAUNCH(ctx, scale_diag_kernel<cxd>, g, 256, 0, (cxd*)d, P, 1.0 + lambda); break;
+    }
+    if (!on_dev) {
+        NQ_CUDA(ctx, cudaMemcpyAsync(S, d, (size_t)P * P * es, cudaMemcpyDeviceToHost, ctx->stream));
+        NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return NQ_OK;
+}
+
 extern "C" int nq_sr_solve(nq_ctx_t ctx, void* S, const void* F, int64_t P, nq_dtype sdtype, double eps, nq_solver algo,
                            double tol, int64_t maxiter, void* dw, int64_t* iters) {
     if (!ctx || !S || !F || !dw || P <= 0) return NQ_ERR_ARG;
@@ -1443,6 +2052,8 @@ extern "C" int nq_sr_solve(nq_ctx_t ctx, void* S, const void* F, int64_t P, nq_d
     const size_t es = nq_dtype_size(sdtype);
     const void* dS = st.in(SL_IN0, S, (size_t)P * P * es);
     const void* dF = st.in(SL_IN1, F, (size_t)P * es);
+    const bool warm = algo == NQ_SOLVE_QLP_WARM;
+    const void* dx0 = warm ? st.in(SL_IN2, dw, (size_t)P * es) : nullptr;     // warm start: dw holds x0 on entry
     void* ddw = st.out(SL_OUT0, dw, (size_t)P * es);
     if (st.status != NQ_OK) return st.status;
     const bool cplx = nq_dtype_is_complex(sdtype);
@@ -1464,19 +2075,36 @@ extern "C" int nq_sr_solve(nq_ctx_t ctx, void* S, const void* F, int64_t P, nq_d
             NQ_LAUNCH(ctx, cxd_to_real_kernel, (unsigned)((nn + 255) / 256), 256, 0, (const cxd*)t, (double*)A, nn);
         }
     }
-    void* b = nq_scratch(ctx, SL_W3, (size_t)2 * P * ws);
+    void* b = nq_scratch(ctx, SL_W3, (size_t)3 * P * ws);
     if (!b) return NQ_ERR_ALLOC;
     void* x = (char*)b + (size_t)P * ws;
+    void* x0w = (char*)b + (size_t)2 * P * ws;
     {
         cxd* t = (cxd*)nq_scratch(ctx, SL_W4, (size_t)P * sizeof(cxd));
         if (!t) return NQ_ERR_ALLOC;
         NQ_LAUNCH(ctx, convert_to_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, dF, t, P, (int)sdtype);
         NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)t, b, P, (int)wdt, 0);
+        if (warm) {
+            NQ_LAUNCH(ctx, convert_to_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, dx0, t, P, (int)sdtype);
+            NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)t, x0w, P, (int)wdt, 0);
+        }
     }
     int status = NQ_OK;
     int64_t its = 0;
-    if (algo == NQ_SOLVE_CHOLESKY) {
-        int* dinfo = (int*)nq_scratch(ctx, SL_W1, 16);
+    if (algo == NQ_SOLVE_QLP || algo == NQ_SOLVE_QLP_WARM) {
+        if (maxiter <= 0) maxiter = 10 * P;
+        int flag = 0;
+        if (cplx) {
+            CgOps<cxd> ops; ops.ctx = ctx; ops.P = P; ops.S = (const cxd*)A; ops.eps = eps;
+            status = qlp_solve<cxd>(ops, (const cxd*)b, warm ? (const cxd*)x0w : nullptr, tol, maxiter, (cxd*)x, &its, &flag);
+        } else {
+            CgOps<double> ops; ops.ctx = ctx; ops.P = P; ops.S = (const double*)A; ops.eps = eps;
+            status = qlp_solve<double>(ops, (const double*)b, warm ? (const double*)x0w : nullptr, tol, maxiter, (double*)x, &its, &flag);
+        }
+        if (status != NQ_OK && status != NQ_ERR_NOT_CONVERGED) return status;
+        if (status == NQ_ERR_NOT_CONVERGED) nq_fail(ctx, status, "MINRES-QLP: iteration limit after %lld iterations", (long long)its);
+    } else if (algo == NQ_SOLVE_CHOLESKY) {
+        int* dinfo = (int*)nq_scratch(ctx, SL_W1, 128);
         if (!dinfo) return NQ_ERR_ALLOC;
         NQ_CUDA(ctx, cudaMemsetAsync(dinfo, 0xff, 4, ctx->stream));
         NQ_CUDA(ctx, cudaMemcpyAsync(x, b, (size_t)P * ws, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1523,8 +2151,9 @@ static int sr_solve_matfree_impl(nq_ctx_t ctx, const void* Oc, int64_t ldO, int6
                                  nq_dtype dtype, const void* F, int real_params, double eps, nq_solver algo, double tol,
                                  int64_t maxiter, void* dw, int64_t* iters) {
     if (!ctx || !Oc || !F || !dw || P <= 0 || Ns <= 0 || ldO < P || Ns_total < Ns) return NQ_ERR_ARG;
-    if (algo != NQ_SOLVE_CG && algo != NQ_SOLVE_MINRES) return nq_fail(ctx, NQ_ERR_ARG, "matrix-free SR needs an iterative solver");
-    const bool mr = algo == NQ_SOLVE_MINRES;
+    if (algo != NQ_SOLVE_CG && algo != NQ_SOLVE_MINRES && algo != NQ_SOLVE_QLP && algo != NQ_SOLVE_QLP_WARM)
+        return nq_fail(ctx, NQ_ERR_ARG, "matrix-free SR needs an iterative solver");
+    const bool mr = algo == NQ_SOLVE_MINRES, qlp = algo == NQ_SOLVE_QLP || algo == NQ_SOLVE_QLP_WARM, warm = algo == NQ_SOLVE_QLP_WARM;
     NQ_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!nq_is_device_ptr(Oc)) return nq_fail(ctx, NQ_ERR_ARG, "Oc must be device-resident");
     const bool out_complex = nq_dtype_is_complex(dtype) && !real_params;
@@ -1533,18 +2162,33 @@ static int sr_solve_matfree_impl(nq_ctx_t ctx, const void* Oc, int64_t ldO, int6
     const size_t ws = nq_dtype_size(wdt);
     NqStage st(ctx);
     const void* dF = st.in(SL_IN0, F, (size_t)P * nq_dtype_size(sdt));
+    const void* dx0 = warm ? st.in(SL_IN2, dw, (size_t)P * nq_dtype_size(sdt)) : nullptr;
     void* ddw = st.out(SL_OUT0, dw, (size_t)P * nq_dtype_size(sdt));
     if (st.status != NQ_OK) return st.status;
-    void* b = nq_scratch(ctx, SL_W0, (size_t)2 * P * ws);
+    void* b = nq_scratch(ctx, SL_W0, (size_t)3 * P * ws);
     cxd* t = (cxd*)nq_scratch(ctx, SL_IN4, (size_t)P * sizeof(cxd));
     if (!b || !t) return NQ_ERR_ALLOC;
     void* x = (char*)b + (size_t)P * ws;
+    void* x0w = (char*)b + (size_t)2 * P * ws;
     NQ_LAUNCH(ctx, convert_to_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, dF, t, P, (int)sdt);
     NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)t, b, P, (int)wdt, 0);
+    if (warm) {
+        NQ_LAUNCH(ctx, convert_to_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, dx0, t, P, (int)sdt);
+        NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)t, x0w, P, (int)wdt, 0);
+    }
     if (maxiter <= 0) maxiter = 10 * P;
     int status;
     int64_t its = 0;
-    if (out_complex) {
+    if (qlp) {
+        int flag = 0;
+        if (out_complex) {
+            CgOps<cxd> ops; ops.ctx = ctx; ops.P = P; ops.eps = eps; ops.O = Oc; ops.ld = ldO; ops.Ns = Ns; ops.Ns_total = Ns_total; ops.odtype = dtype;
+            status = qlp_solve<cxd>(ops, (const cxd*)b, warm ? (const cxd*)x0w : nullptr, tol, maxiter, (cxd*)x, &its, &flag);
+        } else {
+            CgOps<double> ops; ops.ctx = ctx; ops.P = P; ops.eps = eps; ops.O = Oc; ops.ld = ldO; ops.Ns = Ns; ops.Ns_total = Ns_total; ops.odtype = dtype;
+            status = qlp_solve<double>(ops, (const double*)b, warm ? (const double*)x0w : nullptr, tol, maxiter, (double*)x, &its, &flag);
+        }
+    } else if (out_complex) {
         CgOps<cxd> ops; ops.ctx = ctx; ops.P = P; ops.eps = eps; ops.O = Oc; ops.ld = ldO; ops.Ns = Ns; ops.Ns_total = Ns_total; ops.odtype = dtype;
         status = mr ? minres_solve<cxd>(ops, (const cxd*)b, tol, maxiter, (cxd*)x, &its)
                     : cg_solve<cxd>(ops, (const cxd*)b, tol, maxiter, (cxd*)x, &its);
@@ -1554,7 +2198,7 @@ static int sr_solve_matfree_impl(nq_ctx_t ctx, const void* Oc, int64_t ldO, int6
                     : cg_solve<double>(ops, (const double*)b, tol, maxiter, (double*)x, &its);
     }
     if (status != NQ_OK && status != NQ_ERR_NOT_CONVERGED) return status;
-    if (status == NQ_ERR_NOT_CONVERGED) nq_fail(ctx, status, "%s: not converged after %lld iterations", algo == NQ_SOLVE_MINRES ? "MINRES" : "CG", (long long)its);
+    if (status == NQ_ERR_NOT_CONVERGED) nq_fail(ctx, status, "%s: not converged after %lld iterations", qlp ? "MINRES-QLP" : (algo == NQ_SOLVE_MINRES ? "MINRES" : "CG"), (long long)its);
     if (iters) *iters = its;
     NQ_LAUNCH(ctx, convert_to_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const void*)x, t, P, (int)wdt);
     NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)t, ddw, P, (int)sdt, 0);

@@ -10,7 +10,7 @@ from .operators import (LocalOperator as _LocalOperator, KLocalOperatorRow, Liou
 from .machines import RBM, RBMSplit, NDM, af_softplus, af_logcosh, init_random_pars_
 from .samplers import MetropolisSampler, MetropolisSamplerCache, LocalRule, ExactSampler, ExactSamplerCache
 from .algorithms import (SR, Descent, Nesterov, update_, local_scalar, local_grad, stat_analysis, Measurement, sr_cholesky,
-                         sr_cg, sr_minres)
+                         sr_cg, sr_minres, sr_qlp, sr_shift, sr_multiplicative, sr_none)
 from .iterative import BatchedSampler, BatchedObsDMSampler
 from .parallel import shard_chains, init_comm, world_from_env
 from . import models

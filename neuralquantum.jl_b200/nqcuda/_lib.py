@@ -21,7 +21,7 @@ NQ_SOFTPLUS, NQ_LOGCOSH = 0, 1
 NQ_F32, NQ_F64, NQ_C64, NQ_C128 = 0, 1, 2, 3
 NQ_SPIN, NQ_FOCK = 0, 1
 NQ_KET, NQ_SUPER = 0, 1
-NQ_SOLVE_CHOLESKY, NQ_SOLVE_CG, NQ_SOLVE_MINRES = 0, 1, 2
+NQ_SOLVE_CHOLESKY, NQ_SOLVE_CG, NQ_SOLVE_MINRES, NQ_SOLVE_QLP, NQ_SOLVE_QLP_WARM = 0, 1, 2, 3, 4
 NQ_UNIQUE_ID_BYTES = 128
 
 NP_OF = {NQ_F32: np.float32, NQ_F64: np.float64, NQ_C64: np.complex64, NQ_C128: np.complex128}
@@ -108,6 +108,7 @@ _PROTOS = {
     "nq_force_liouvillian": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, C.POINTER(_dbl)]),
     "nq_sr_setup": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i32, _vp, _vp]),
     "nq_sr_solve": (_i32, [_vp, _vp, _vp, _i64, _i32, _dbl, _i32, _dbl, _i64, _vp, C.POINTER(_i64)]),
+    "nq_sr_scale_diagonal": (_i32, [_vp, _vp, _i64, _i32, _dbl]),
     "nq_sr_solve_matfree": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i32, _dbl, _dbl, _i64, _vp,
                                    C.POINTER(_i64)]),
     "nq_sr_solve_matfree_algo": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i32, _dbl, _i32, _dbl, _i64, _vp,

@@ -11,8 +11,8 @@ import numpy as np
 
 from . import _lib as L
 
-sr_cholesky, sr_cg, sr_minres = "sr_cholesky", "sr_cg", "sr_minres"
-sr_shift = "sr_shift"
+sr_cholesky, sr_cg, sr_minres, sr_qlp = "sr_cholesky", "sr_cg", "sr_minres", "sr_qlp"
+sr_shift, sr_multiplicative, sr_none = "sr_shift", "sr_multiplicative", "sr_none"
 
 
 def local_scalar(net, op, sigma):
@@ -60,18 +60,35 @@ def stat_analysis(ctx, vals):
 
 
 class SR:
-    """SR(T=Float32; eps=0.001, precision=1e-4, algorithm=sr_cholesky, full_matrix=false).
-    eps and precision are stored in precision T exactly like the reference (quirk Q16)."""
+    """SR(T=Float32; eps=0.001, precision=1e-4, precondition_type=sr_shift, algorithm=sr_cholesky, full_matrix=false,
+    lambda0=100, b=0.95, lambda_min=1e-4)  (SR/SR.jl:37-57).  eps, precision and the multiplicative-regulariser
+    constants are stored in precision T exactly like the reference (quirk Q16).
+    precondition_type: sr_shift (S + eps I), sr_multiplicative (S + lambda Diagonal(diag S), lambda = max(lambda0 b^iter,
+    lambda_min); explicit S only) or sr_none.  algorithm: sr_cholesky | sr_cg | sr_minres | sr_qlp."""
 
     def __init__(self, T=np.float32, eps=0.001, precision=10e-5, algorithm=sr_cholesky, full_matrix=False,
-                 precondition_type=sr_shift):
-        if precondition_type != sr_shift:
-            raise NotImplementedError("only sr_shift is on the built path (SURVEY 8f)")
-        if algorithm not in (sr_cholesky, sr_cg, sr_minres):
-            raise NotImplementedError("sr_cholesky, sr_cg and sr_minres are on the built path (SURVEY 8f)")
-        self.sr_diag_shift = float(np.dtype(T).type(eps))
-        self.sr_precision = float(np.dtype(T).type(precision))
-        self.algorithm, self.full_matrix = algorithm, full_matrix
+                 precondition_type=sr_shift, lambda0=100.0, b=0.95, lambda_min=1e-4, maxiter=None):
+        if precondition_type not in (sr_shift, sr_multiplicative, sr_none):
+            raise ValueError("precondition_type: sr_shift, sr_multiplicative or sr_none")
+        if algorithm not in (sr_cholesky, sr_cg, sr_minres, sr_qlp):
+            raise NotImplementedError("sr_cholesky, sr_cg, sr_minres and sr_qlp are built (sr_diag / sr_div / sr_lsq: SURVEY 8f)")
+        if precondition_type == sr_multiplicative and not (algorithm == sr_cholesky or full_matrix):
+            raise ValueError("sr_multiplicative needs the explicit S (sr_cholesky or full_matrix=True): diag(S) of the "
+                             "matrix-free operator is not defined in the reference either (SR_notfull.jl)")
+        t = np.dtype(T).type
+        self.sr_diag_shift = float(t(eps))
+        self.sr_precision = float(t(precision))
+        self.lambda0, self.b, self.lambda_min = float(t(lambda0)), float(t(b)), float(t(lambda_min))
+        self.algorithm, self.full_matrix, self.precondition_type = algorithm, full_matrix, precondition_type
+        self.maxiter = 0 if maxiter is None else int(maxiter)      # 0 = the reference's fixed 10 P (SRIterative.jl:95)
+
+    def regulariser(self, iter_n):
+        """(eps, lambda) applied at iteration iter_n: S + eps I + lambda Diagonal(diag S)."""
+        if self.precondition_type == sr_shift:
+            return self.sr_diag_shift, 0.0
+        if self.precondition_type == sr_multiplicative:
+            return 0.0, max(self.lambda0 * self.b ** iter_n, self.lambda_min)
+        return 0.0, 0.0
 
 
 class Descent:

@@ -13,7 +13,9 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from .algorithms import Measurement, SR, sr_cg, sr_cholesky, sr_minres, stat_analysis
+import warnings
+
+from .algorithms import Measurement, SR, sr_cg, sr_cholesky, sr_minres, sr_qlp, stat_analysis
 from .operators import Liouvillian
 from .samplers import ExactSampler, ExactSamplerCache, MetropolisSamplerCache
 
@@ -198,24 +200,44 @@ class BatchedSampler:
         return stat, self
 
     def precondition_(self, iter_n=1):
-        """precondition!(cache, algo, iter) -> dw (device tensor; .cpu().numpy() for the host copy)."""
+        """precondition!(cache, algo, iter) -> dw (device tensor; .cpu().numpy() for the host copy).
+        Iterative solvers follow SRIterative.jl:71-153: one run of the chosen solver (maxiter 10 P, tol = precision);
+        if it did not converge, up to 5 MINRES-QLP runs warm-started from the current dw with the solver's default
+        tolerance sqrt(eps(T)) (the restart call passes none), a warning each; still not converged -> dw = 0.
+        (In the reference that ladder cannot run: its restart call has one positional argument too many, and sr_qlp
+        itself reports every exit as converged -- quirk Q22 in oracle/minresqlp.py.  This is the ladder the code spells.)"""
         ctx, P, algo = self.ctx, self.net.P, self.algo
         its = C.c_int64()
         sd = L.nq_dtype(self.sdtype)
-        solver = {sr_cholesky: L.NQ_SOLVE_CHOLESKY, sr_cg: L.NQ_SOLVE_CG, sr_minres: L.NQ_SOLVE_MINRES}[algo.algorithm]
-        if self.S is not None:
-            st = L.lib.nq_sr_solve(ctx.h, self.S.data_ptr(), self.F.data_ptr(), P, sd, algo.sr_diag_shift, solver,
-                                   algo.sr_precision, 0, self.dw.data_ptr(), C.byref(its))
-        else:
-            st = L.lib.nq_sr_solve_matfree_algo(ctx.h, self.O.data_ptr(), P, P, self.Ns, self.Ns_total,
-                                                L.nq_dtype(self.net.out_dtype), self.F.data_ptr(), int(self.real_params),
-                                                algo.sr_diag_shift, solver, algo.sr_precision, 0, self.dw.data_ptr(),
-                                                C.byref(its))
-        self.last_iters = its.value
-        if st == L.NQ_ERR_NOT_CONVERGED:       # reference: zero update after failed restarts
-            self.dw.zero_()
-        else:
-            L.check(st, ctx.h)
+        solver = {sr_cholesky: L.NQ_SOLVE_CHOLESKY, sr_cg: L.NQ_SOLVE_CG, sr_minres: L.NQ_SOLVE_MINRES,
+                  sr_qlp: L.NQ_SOLVE_QLP}[algo.algorithm]
+        eps, lam = algo.regulariser(iter_n)
+        if lam != 0.0:      # sr_multiplicative (explicit S only): S + lambda Diagonal(diag S)
+            L.check(L.lib.nq_sr_scale_diagonal(ctx.h, self.S.data_ptr(), P, sd, lam), ctx.h)
+
+        def run(solver_code, tol):
+            if self.S is not None:
+                return L.lib.nq_sr_solve(ctx.h, self.S.data_ptr(), self.F.data_ptr(), P, sd, eps, solver_code, tol, algo.maxiter,
+                                         self.dw.data_ptr(), C.byref(its))
+            return L.lib.nq_sr_solve_matfree_algo(ctx.h, self.O.data_ptr(), P, P, self.Ns, self.Ns_total,
+                                                  L.nq_dtype(self.net.out_dtype), self.F.data_ptr(),
+                                                  int(self.real_params), eps, solver_code, tol, algo.maxiter, self.dw.data_ptr(),
+                                                  C.byref(its))
+        st = run(solver, algo.sr_precision)
+        self.last_iters, self.restarts, self.converged = its.value, 0, st == L.NQ_OK
+        if st == L.NQ_ERR_NOT_CONVERGED:
+            default_tol = float(np.sqrt(np.finfo(np.dtype(self.net.rdtype)).eps))
+            while st == L.NQ_ERR_NOT_CONVERGED and self.restarts < 5:
+                self.restarts += 1
+                warnings.warn("minresqlp not converged. Additional %d iters for the %d time." % (10 * P, self.restarts))
+                st = run(L.NQ_SOLVE_QLP_WARM, default_tol)
+                self.last_iters += its.value
+            self.converged = st == L.NQ_OK
+            if st == L.NQ_ERR_NOT_CONVERGED:       # success = false; dw .= 0.0
+                with _torch().cuda.stream(ctx.torch_stream()):
+                    self.dw.zero_()
+                return self.dw
+        L.check(st, ctx.h)
         return self.dw
 
     def update_(self, opt, dw=None):

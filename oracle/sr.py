@@ -36,6 +36,50 @@ def force_liouvillian(Lloc, gLloc, O_avg):
     return g.conj()
 
 
+# ---- the same three formulas accumulated in extended precision (x87 long double) --------------------------------
+# The force is an average of O(1) terms that cancels to a small fraction of their size; numpy's float64 reductions
+# carry an error ~1e-16 * log2(Ns) * sum|terms| -- the same order as the 1e-11 element-wise parity bound once the
+# cancellation is counted.  The parity tests therefore compare the device (double-double accumulation) against these.
+_LD = np.longdouble
+
+
+def _ld_wsum(w, X):
+    """sum_s w_s X[k, s] for complex w [Ns], X [P, Ns] in long double; returns (re, im) long double arrays."""
+    wr, wi = np.real(w).astype(_LD), np.imag(w).astype(_LD)
+    Xr, Xi = np.real(X).astype(_LD), np.imag(X).astype(_LD)
+    return Xr @ wr - Xi @ wi, Xr @ wi + Xi @ wr
+
+
+def center_ld(O):
+    Or, Oi = np.real(O).astype(_LD), np.imag(O).astype(_LD)
+    ar, ai = Or.mean(axis=1), Oi.mean(axis=1)
+    return (ar, ai), (Or - ar[:, None], Oi - ai[:, None])
+
+
+def force_ket_ld(Eloc, O):
+    """force_ket(Eloc, O - <O>) from the UNcentred O, accumulated in long double; complex128 result.
+    F_k = (1/Ns) sum_s E_s conj(Oc_ks)."""
+    Ns = O.shape[1]
+    _, (cr, ci) = center_ld(O)
+    er, ei = np.real(Eloc).astype(_LD), np.imag(Eloc).astype(_LD)
+    re = (cr @ er + ci @ ei) / Ns                  # Re[E conj(Oc)] = Er Or + Ei Oi
+    im = (cr @ ei - ci @ er) / Ns                  # Im[E conj(Oc)] = Ei Or - Er Oi
+    return np.asarray(re, dtype=np.float64) + 1j * np.asarray(im, dtype=np.float64)
+
+
+def force_liouvillian_ld(Lloc, gLloc, O):
+    """force_liouvillian(Lloc, gLloc, <O>) with <O> from the uncentred O, accumulated in long double.
+    F_k = conj( (1/Ns) sum_s L_s conj(gL_ks) - C conj(<O_k>) ),  C = <|L|^2>."""
+    Ns = gLloc.shape[1]
+    (ar, ai), _ = center_ld(O)
+    lr, li = np.real(Lloc).astype(_LD), np.imag(Lloc).astype(_LD)
+    gr, gi = np.real(gLloc).astype(_LD), np.imag(gLloc).astype(_LD)
+    C = np.mean(lr * lr + li * li)
+    re = (gr @ lr + gi @ li) / Ns - C * ar         # Re[L conj(gL)] - C Re[conj(avg)]
+    im = (gr @ li - gi @ lr) / Ns + C * ai         # Im[L conj(gL)] - C Im[conj(avg)]
+    return np.asarray(re, dtype=np.float64) - 1j * np.asarray(im, dtype=np.float64)
+
+
 def sr_setup(Oc, gradC, real_params):
     """SRDirect.jl:26-49.  real_params: S = Re(Oc Oc^H)/Ns, F = Re(gradC);
     complex: S = conj(Oc Oc^H)/Ns, F = gradC."""
