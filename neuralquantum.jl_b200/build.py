@@ -49,6 +49,7 @@ def build(force=False, verbose=False):
     inc = ["-I", _nccl_include()]
     # the linked library is newer than every source: nothing to do (object files do not travel to the GPU box)
     if not force and os.path.exists(LIB) and not _stale(LIB, srcs + hdrs):
+        build_cabi_smoke()
         return LIB
     jobs = []
     for s in srcs:
@@ -73,7 +74,23 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+    build_cabi_smoke()
     return LIB
+
+
+def build_cabi_smoke():
+    """tests/cabi_smoke: a plain-C host of the ABI (gcc, host buffers only), run by tests/test_gpu_cabi_c.py."""
+    src = os.path.join(HERE, "..", "tests", "cabi_smoke.c")
+    exe = os.path.join(HERE, "..", "tests", "cabi_smoke")
+    if not os.path.exists(src) or (os.path.exists(exe) and not _stale(exe, [src, LIB])):
+        return exe
+    cmd = ["gcc", "-O2", "-std=c11", src, "-I", os.path.join(HERE, "..", "include"), "-L", HERE, "-lnqcuda", "-lm",
+           "-Wl,-rpath,$ORIGIN/../neuralquantum.jl_b200", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("gcc failed on tests/cabi_smoke.c")
+    return exe
 
 
 if __name__ == "__main__":

@@ -6,7 +6,8 @@
 enum {
     SL_IN0 = 0, SL_IN1, SL_IN2, SL_IN3, SL_IN4,
     SL_OUT0, SL_OUT1, SL_OUT2, SL_OUT3,
-    SL_PROW, SL_PCOL, SL_LOGPSI, SL_W0, SL_W1, SL_W2, SL_W3, SL_W4, SL_W5
+    SL_PROW, SL_PCOL, SL_LOGPSI, SL_W0, SL_W1, SL_W2, SL_W3, SL_W4, SL_W5,
+    SL_HOSTO, SL_HOSTG          // device copies of host-resident O / grad L_loc matrices (SR entry points)
 };
 
 struct nq_machine_s {

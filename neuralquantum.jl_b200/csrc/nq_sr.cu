@@ -1847,10 +1847,26 @@ extern "C" int nq_abs2(nq_ctx_t ctx, const void* vals, int64_t n, nq_dtype vdtyp
     return st.finish();
 }
 
-extern "C" int nq_center(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype, void* avg) {
-    if (!ctx || !O || !avg || P <= 0 || Ns <= 0 || ldO < P) return NQ_ERR_ARG;
+// The SR entry points take the [P, Ns] matrices where the caller keeps them.  Device-resident (the iteration driver):
+// used in place.  Host-resident (a Julia Array / C buffer): copied to a device scratch slot first.
+static const void* sr_matrix_on_device(nq_ctx_t ctx, int slot, const void* X, int64_t ld, int64_t Ns, nq_dtype dtype, int* status) {
+    *status = NQ_OK;
+    if (nq_is_device_ptr(X)) return X;
+    const size_t bytes = (size_t)ld * Ns * nq_dtype_size(dtype);
+    void* d = nq_scratch(ctx, slot, bytes);
+    if (!d) { *status = NQ_ERR_ALLOC; return nullptr; }
+    cudaError_t e = cudaMemcpyAsync(d, X, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { *status = nq_fail(ctx, NQ_ERR_CUDA, "H2D copy of O: %s", cudaGetErrorString(e)); return nullptr; }
+    return d;
+}
+
+extern "C" int nq_center(nq_ctx_t ctx, void* O_user, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype, void* avg) {
+    if (!ctx || !O_user || !avg || P <= 0 || Ns <= 0 || ldO < P) return NQ_ERR_ARG;
     NQ_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!nq_is_device_ptr(O)) return nq_fail(ctx, NQ_ERR_ARG, "nq_center works in place on a device-resident O");
+    int hs = NQ_OK;
+    void* O = const_cast<void*>(sr_matrix_on_device(ctx, SL_HOSTO, O_user, ldO, Ns, dtype, &hs));
+    if (hs != NQ_OK) return hs;
+    const bool o_on_host = O != O_user;
     NqStage st(ctx);
     void* davg = st.out(SL_OUT0, avg, (size_t)P * nq_dtype_size(dtype));
     cxd* a = (cxd*)nq_scratch(ctx, SL_W0, (size_t)P * sizeof(cxd));
@@ -1876,6 +1892,10 @@ extern "C" int nq_center(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, int64_t 
         default: NQ_LAUNCH(ctx, subtract_avg_kernel<cxd>, grid, 128, 0, (cxd*)O, ldO, P, Ns, (const cxd*)a); break;
     }
     NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)a, davg, P, (int)dtype, 0);
+    if (o_on_host) {      // centred O goes back to the caller's array (the reference centres in place)
+        NQ_CUDA(ctx, cudaMemcpyAsync(O_user, O, (size_t)ldO * Ns * nq_dtype_size(dtype), cudaMemcpyDeviceToHost, ctx->stream));
+        NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return st.finish();
 }
 
@@ -1883,7 +1903,9 @@ extern "C" int nq_force_ket(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P
                             const void* Eloc, void* gradC) {
     if (!ctx || !Oc || !Eloc || !gradC || P <= 0 || Ns <= 0 || ldO < P) return NQ_ERR_ARG;
     NQ_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!nq_is_device_ptr(Oc)) return nq_fail(ctx, NQ_ERR_ARG, "Oc must be device-resident");
+    int hs = NQ_OK;
+    Oc = sr_matrix_on_device(ctx, SL_HOSTO, Oc, ldO, Ns, dtype, &hs);
+    if (hs != NQ_OK) return hs;
     NqStage st(ctx);
     nq_dtype cdt = nq_complex_of(dtype);
     const void* dE = st.in(SL_IN0, Eloc, (size_t)Ns * nq_dtype_size(cdt));
@@ -1901,8 +1923,10 @@ extern "C" int nq_force_liouvillian(nq_ctx_t ctx, const void* Lloc, const void* 
                                     nq_dtype dtype, const void* avg, void* gradC, double* cost) {
     if (!ctx || !Lloc || !gLloc || !avg || !gradC || P <= 0 || Ns <= 0 || ld < P) return NQ_ERR_ARG;
     NQ_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!nq_is_device_ptr(gLloc)) return nq_fail(ctx, NQ_ERR_ARG, "grad L_loc must be device-resident");
     if (!nq_dtype_is_complex(dtype)) return nq_fail(ctx, NQ_ERR_ARG, "L_loc / grad L_loc are complex");
+    int hs = NQ_OK;
+    gLloc = sr_matrix_on_device(ctx, SL_HOSTG, gLloc, ld, Ns, dtype, &hs);
+    if (hs != NQ_OK) return hs;
     NqStage st(ctx);
     size_t cs = nq_dtype_size(dtype);
     const void* dL = st.in(SL_IN0, Lloc, (size_t)Ns * cs);
@@ -1942,7 +1966,9 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
                            nq_dtype dtype, const void* gradC, int real_params, void* S, void* F) {
     if (!ctx || !Oc || !gradC || !S || !F || P <= 0 || Ns <= 0 || ldO < P || Ns_total < Ns) return NQ_ERR_ARG;
     NQ_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!nq_is_device_ptr(Oc)) return nq_fail(ctx, NQ_ERR_ARG, "Oc must be device-resident");
+    int hs = NQ_OK;
+    Oc = sr_matrix_on_device(ctx, SL_HOSTO, Oc, ldO, Ns, dtype, &hs);
+    if (hs != NQ_OK) return hs;
     const bool ocx = nq_dtype_is_complex(dtype);
     const bool out_complex = ocx && !real_params;
     // S/F dtype: real nets -> real of the same precision; complex nets -> complex
@@ -2155,7 +2181,9 @@ static int sr_solve_matfree_impl(nq_ctx_t ctx, const void* Oc, int64_t ldO, int6
         return nq_fail(ctx, NQ_ERR_ARG, "matrix-free SR needs an iterative solver");
     const bool mr = algo == NQ_SOLVE_MINRES, qlp = algo == NQ_SOLVE_QLP || algo == NQ_SOLVE_QLP_WARM, warm = algo == NQ_SOLVE_QLP_WARM;
     NQ_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!nq_is_device_ptr(Oc)) return nq_fail(ctx, NQ_ERR_ARG, "Oc must be device-resident");
+    int hs = NQ_OK;
+    Oc = sr_matrix_on_device(ctx, SL_HOSTO, Oc, ldO, Ns, dtype, &hs);
+    if (hs != NQ_OK) return hs;
     const bool out_complex = nq_dtype_is_complex(dtype) && !real_params;
     nq_dtype sdt = out_complex ? dtype : nq_real_of(dtype);
     nq_dtype wdt = out_complex ? NQ_C128 : NQ_F64;
