@@ -60,10 +60,14 @@ typedef enum { NQ_KET = 0, NQ_SUPER = 1 } nq_space;                      /* H on
  * (the warm-started restarts of SRIterative.jl:133-150). */
 typedef enum { NQ_SOLVE_CHOLESKY = 0, NQ_SOLVE_CG = 1, NQ_SOLVE_MINRES = 2, NQ_SOLVE_QLP = 3, NQ_SOLVE_QLP_WARM = 4 } nq_solver;
 
+/* ref: Samplers/MCMCRules/{LocalRule,ExchangeRule,Nagy,OperatorRule}.jl */
+typedef enum { NQ_RULE_LOCAL = 0, NQ_RULE_EXCHANGE = 1, NQ_RULE_NAGY = 2, NQ_RULE_OPERATOR = 3 } nq_rule;
+
 typedef struct nq_ctx_s* nq_ctx_t;
 typedef struct nq_machine_s* nq_machine_t;
 typedef struct nq_operator_s* nq_operator_t;
 typedef struct nq_sampler_s* nq_sampler_t;
+typedef struct nq_symm_s* nq_symm_t;
 
 /* ======================================================================================
  * Context.  One context = one device + one stream.  ref: one sampler object per task/rank
@@ -204,6 +208,63 @@ int nq_sampler_replay(nq_sampler_t s, const int32_t* sites, const void* uniforms
 int nq_sampler_sample(nq_sampler_t s, int burn, int L, uint64_t* prow, uint64_t* pcol,
                       void* srow, void* scol, nq_dtype sdtype);
 int nq_sampler_counters(nq_sampler_t s, int64_t* passes_done, int64_t* passes_accepted);
+/* Transition rule of the chain (default NQ_RULE_LOCAL).
+ *   NQ_RULE_EXCHANGE (ket machines): a random couple (i, j) of `couplings` [n_couplings][2] (int32, 0-based) is swapped.
+ *                    ref: MCMCRules/ExchangeRule.jl:14-68 (couples = the 2-site couplings of an operator)
+ *   NQ_RULE_NAGY (density-matrix machines): one of 8 moves -- hopping in sigma / sigma' (site s and one element of the
+ *                    s-th couple, the reference indexes its couple list by SITE), single flips, the dissipator move
+ *                    (an empty Fock site is excited with probability 1/10), the jumper.  ref: MCMCRules/Nagy.jl:40-115
+ *   NQ_RULE_OPERATOR: a uniformly drawn connection of `op` (diagonal and zero elements included, reference order) is
+ *                    applied; log_prob_bias = log(n_forward / n_back) enters the accept test.
+ *                    ref: MCMCRules/OperatorRule.jl:27-59, Metropolis.jl:148
+ * These rules flip several sites per proposal: the chain re-evaluates the activations of the moved pre-activations. */
+int nq_sampler_set_rule(nq_sampler_t s, nq_rule rule, int n_couplings, const int32_t* couplings, nq_operator_t op);
+/* one samplenext! of a non-local rule with supplied randomness: draws [passes,B,4] int32 = the integers the reference
+ * draws per proposal (1-based): Exchange (couple, -, -, -); Nagy (move 1..8, site 1..N, aux, aux2) with aux = element
+ * 1..2 of the couple (moves 1-4), rand(1:10) of the row (move 7; aux2 = that of the column), column site (move 8);
+ * Operator (r, -, -, -): r is the raw 32-bit random, the connection index is floor(r n_forward / 2^32).
+ * uniforms / accept_out as in nq_sampler_replay. */
+int nq_sampler_replay_rule(nq_sampler_t s, const int32_t* draws, const void* uniforms, uint8_t* accept_out);
+
+/* ======================================================================================
+ * Symmetrised machines (NDMSymm): a bare machine whose parameters are tied by site permutations.
+ * The handle owns the Ps symmetric parameters (machine dtype, real) and two maps:
+ *   parameters:  bare[q] = w[src[q]]   after the ranges avg_ranges[i] = [a, b) of w were replaced by their mean
+ *                (set_bare_params!, NDMSymm.jl:79-128: the local biases b_mu, b_lam are averaged)
+ *   gradients:   Osymm[p, s] = scale[p] * sum_{e in [ptr[p], ptr[p+1])} Obare[idx[e], s]
+ *                (symmetrize_grad_NDM_batched!, NDMSymmBatched.jl:22-36 with the 0/1 matrices of NDMSymm.jl:130-181)
+ * All index arrays are HOST arrays, 0-based.  The bare machine must outlive the handle.
+ * ==================================================================================== */
+int nq_symm_create(nq_machine_t bare, int64_t Ps, const int64_t* ptr, const int32_t* idx, const double* scale,
+                   const int32_t* src, int n_avg, const int64_t* avg_ranges, nq_symm_t* out);
+int nq_symm_destroy(nq_symm_t g);
+int nq_symm_nparams(nq_symm_t g, int64_t* Ps);
+int nq_symm_set_params(nq_symm_t g, const void* w, int64_t Ps);    /* stores w, averages, expands into the bare machine */
+int nq_symm_get_params(nq_symm_t g, void* w, int64_t Ps);
+/* update!(opt, cnet::NDMSymm, dw): w <- w - eta dw, then set_bare_params! (NDMSymm.jl:27-30) */
+int nq_symm_update(nq_symm_t g, const void* dw, double eta);
+/* rows of the bare gradient [Pb, Ns] (ldb) -> rows of the symmetrised gradient [Ps, Ns] (lds); dtype = element type */
+int nq_symm_gradient(nq_symm_t g, const void* Obare, int64_t ldb, int64_t Ns, nq_dtype dtype, void* Osymm, int64_t lds);
+
+/* ======================================================================================
+ * Full-space tools (the reference's validation path; indexable spaces: at most 2^30 table entries).
+ * Basis number i (1-based) <-> digits of i-1, site 1 least significant (Hilbert/HomogeneousSpin.jl:156-179);
+ * density matrices: super index = (col-1) D + row, D = 2^N.
+ * ==================================================================================== */
+int nq_fullspace_size(nq_machine_t m, int64_t* size);          /* 2^N (RBM) or 4^N (RBMSplit, NDM) */
+/* ket(net, hilb, norm) / densitymatrix(net, hilb, norm): out[i] = exp(log psi(state i)), [2^N] or column-major [D,D]
+ * (rho[row,col]) of out_type; norm != 0 divides the ket by its 2-norm and the density matrix by its trace.
+ * ref: utils/densitymatrix.jl:9-62 */
+int nq_fullspace_state(nq_machine_t m, int norm, void* out);
+/* ExactSampler init_sampler!: cdf[i] = sum_{k<=i} p_k / sum_k p_k with p_k = exp(log_prob_psi(k)) (evaluated as
+ * exp(lp - max lp)), [size] doubles.  ref: Samplers/Exact.jl:135-162 */
+int nq_exact_table(nq_machine_t m, double* cdf);
+/* ExactSampler samplenext! for L slots x B chains: basis number = searchsortedfirst(cdf, r), written as packed words
+ * [L][B] (pcol NULL for RBM) and optionally as 1-based numbers in `indices` [L][B].  r comes from `uniforms` [L][B]
+ * doubles when given (replay), else from Philox4x32-10 keyed by (seed, chain_offset + chain) at counter
+ * draw_base + slot -- independent of how chains are sharded.  ref: Samplers/Exact.jl:166-181 */
+int nq_exact_sample(nq_machine_t m, const double* cdf, uint64_t seed, int64_t chain_offset, uint64_t draw_base,
+                    int64_t B, int64_t L, const double* uniforms, uint64_t* prow, uint64_t* pcol, int64_t* indices);
 
 /* ======================================================================================
  * Stochastic reconfiguration.

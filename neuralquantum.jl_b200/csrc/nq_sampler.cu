@@ -12,6 +12,7 @@
 // Accept rule (Metropolis.jl:148-154): accept iff  u - exp(logp' - logp) < 0,  logp = 2 Re log psi,
 // evaluated in the machine's real precision.
 #include "nq_internal.cuh"
+#include "nq_opdev.cuh"
 
 struct nq_sampler_s {
     nq_ctx_t ctx;
@@ -26,6 +27,11 @@ struct nq_sampler_s {
     uint64_t* pcol;
     unsigned long long* accepted;   // device counter
     int64_t passes_done;
+    // transition rule (nq_sampler_set_rule): couplings of Exchange / Nagy, operator of the OperatorRule
+    int rule;
+    int n_coup;
+    int32_t* coup;            // device [n_coup][2], 0-based sites
+    nq_operator_t rule_op;
 };
 
 namespace {
@@ -85,6 +91,9 @@ struct RunArgs {
     uint64_t* out_prow;        // [L][B][W64]
     uint64_t* out_pcol;
     unsigned long long* accepted;
+    int rule, n_coup;
+    const int32_t* coup;
+    const int32_t* draws;      // replay of a rule: [passes][B][4]
 };
 
 template <typename T>
@@ -350,6 +359,296 @@ __global__ void sampler_ndm_kernel(const T* __restrict__ par, const T* __restric
     }
 }
 
+
+// ---- transition rules other than LocalRule ------------------------------------------------
+// ExchangeRule (MCMCRules/ExchangeRule.jl:36-68, ket states), NagyRule (Nagy.jl:40-115, doubled states) and
+// OperatorRule (OperatorRule.jl:27-59: a uniformly drawn connection of the operator, log_prob_bias =
+// log(n_forward / n_back)).  Proposals flip several sites, so this kernel tracks the pre-activations theta_k of
+// every unit and re-evaluates f on theta_k + sum_flips dv W_kj (O(units) transcendentals per proposal, in double
+// precision whatever the machine's type; the accept test is rounded to the machine's real type like the reference).
+// One warp per chain, all lanes build the proposal redundantly (integer work on the same addresses).
+//   log p = lin + sum_k c_k Re f(theta_k):   RBM/RBMSplit c = 2, lin = 2 Re(a.v);   NDM: lambda units of sigma and
+//   sigma' (c = 1, real), ancillas (c = 2, complex), lin = b_lam.(v + v').
+constexpr int MAXFLIP = 16;
+
+__device__ __forceinline__ cxd as_cxd(float a) { return cxd((double)a, 0.0); }
+__device__ __forceinline__ cxd as_cxd(double a) { return cxd(a, 0.0); }
+template <typename T> __device__ __forceinline__ cxd as_cxd(cx<T> a) { return cxd((double)a.re, (double)a.im); }
+
+template <typename E, int KIND>
+struct Units {
+    const E* par; int N, M, A;
+    __device__ __forceinline__ int count() const { return KIND == NQ_NDM ? 2 * M + A : M; }
+    // weight of a unit in log p and whether its pre-activation is complex
+    __device__ __forceinline__ double weight(int k) const { return (KIND == NQ_NDM && k < 2 * M) ? 1.0 : 2.0; }
+    __device__ __forceinline__ cxd bias(int k) const {
+        if (KIND == NQ_RBM) return as_cxd(par[N + k]);
+        if (KIND == NQ_RBMSPLIT) return as_cxd(par[2 * N + k]);
+        const int64_t MN = (int64_t)M * N, AN = (int64_t)A * N;
+        const int64_t o_hlam = (N + M + MN + AN) + N, o_dlam = o_hlam + M;
+        if (k < 2 * M) return as_cxd(par[o_hlam + (k < M ? k : k - M)]);
+        return as_cxd(par[o_dlam + (k - 2 * M)]);
+    }
+    // d theta_k / d value of site j on side `side`
+    __device__ __forceinline__ cxd slope(int k, int side, int j) const {
+        if (KIND == NQ_RBM) return as_cxd(par[N + M + k + (int64_t)M * j]);
+        if (KIND == NQ_RBMSPLIT) return as_cxd(par[2 * N + M + (side ? (int64_t)M * N : 0) + k + (int64_t)M * j]);
+        const int64_t MN = (int64_t)M * N, AN = (int64_t)A * N;
+        const int64_t o_umu = N + M + MN, o_wlam = o_umu + AN + N + M + A, o_ulam = o_wlam + MN;
+        if (k < M) return side == 0 ? as_cxd(par[o_wlam + k + (int64_t)M * j]) : cxd(0.0, 0.0);
+        if (k < 2 * M) return side == 1 ? as_cxd(par[o_wlam + (k - M) + (int64_t)M * j]) : cxd(0.0, 0.0);
+        const int q = k - 2 * M;
+        const double ul = 0.5 * (double)real_part(par[o_ulam + q + (int64_t)A * j]), um = 0.5 * (double)real_part(par[o_umu + q + (int64_t)A * j]);
+        return cxd(ul, side == 0 ? um : -um);
+    }
+    // d lin / d value of site j on side `side`
+    __device__ __forceinline__ double lin_slope(int side, int j) const {
+        if (KIND == NQ_RBM) return 2.0 * (double)real_part(par[j]);
+        if (KIND == NQ_RBMSPLIT) return 2.0 * (double)real_part(par[(side ? N : 0) + j]);
+        const int64_t o_blam = N + M + (int64_t)M * N + (int64_t)A * N;
+        return (double)real_part(par[o_blam + j]);
+    }
+};
+
+template <int ACT>
+__device__ __forceinline__ double unit_value(cxd th, bool is_real) {
+    if (is_real) { double f, d; act_eval<ACT>(th.re, f, d); return f; }
+    cxd f, d;
+    act_eval<ACT>(th, f, d);
+    return f.re;
+}
+
+struct Proposal { int n; int idx[MAXFLIP]; double bias; };   // idx = side * N + site
+
+__device__ __forceinline__ void toggle(uint64_t* m, int j) { m[j >> 6] ^= 1ull << (j & 63); }
+
+// number of connections of (rb, cb) in reference order (zero matrix elements included: length(row_valdiff!(...)))
+__device__ int op_count(const OpDev& op, const uint64_t* rb, const uint64_t* cb) {
+    int n = 0;
+    for (int t = 0; t < op.n_terms; t++) visit_term(op, t, rb, cb, [&](double, double, int, uint32_t, int, uint32_t) { n++; });
+    return n;
+}
+// flip masks of connection number `pick`
+__device__ void op_pick(const OpDev& op, const uint64_t* rb, const uint64_t* cb, int pick, uint64_t* fr, uint64_t* fc) {
+    int n = 0;
+    for (int t = 0; t < op.n_terms; t++)
+        visit_term(op, t, rb, cb, [&](double, double, int L, uint32_t fl, int R, uint32_t frr) {
+            if (n == pick) {
+                if (L >= 0) {
+                    const int32_t* s = op.part_sites + op.part_site_ptr[L];
+                    for (int i = 0; fl >> i; i++) if ((fl >> i) & 1u) toggle(fr, s[i]);
+                }
+                if (R >= 0) {
+                    const int32_t* s = op.part_sites + op.part_site_ptr[R];
+                    for (int i = 0; frr >> i; i++) if ((frr >> i) & 1u) toggle(fc, s[i]);
+                }
+            }
+            n++;
+        });
+}
+
+// d[0..3]: production = raw 32-bit randoms; replay = the reference's integer draws (1-based), see nq_sampler_replay_rule
+template <bool DOUBLED>
+__device__ void make_proposal(const RunArgs& a, const OpDev& op, bool replay, const uint32_t (&d)[4], const uint64_t* rb,
+                              const uint64_t* cb, Proposal& p) {
+    const int N = a.N, W64 = (N + 63) >> 6;
+    uint64_t fr[MAXW], fc[MAXW];
+#pragma unroll
+    for (int w = 0; w < MAXW; w++) { fr[w] = 0; fc[w] = 0; }
+    p.bias = 0.0;
+    auto pick = [&](uint32_t raw, int range) { return replay ? (int)raw - 1 : (int)(((uint64_t)raw * (uint64_t)range) >> 32); };
+    if (a.rule == NQ_RULE_EXCHANGE) {
+        const int c = pick(d[0], a.n_coup);
+        const int i = a.coup[2 * c], j = a.coup[2 * c + 1];
+        if (get_bit(rb, i) != get_bit(rb, j)) { toggle(fr, i); toggle(fr, j); }
+    } else if (a.rule == NQ_RULE_NAGY) {
+        const int move = pick(d[0], 8) + 1;
+        const int s1 = pick(d[1], N);
+        if (move <= 4) {                               // hopping in sigma (1, 2) or sigma' (3, 4)
+            const int s2 = a.coup[2 * s1 + pick(d[2], 2)];       // rand(adjacency_list[s1]): one element of the s1-th couple
+            uint64_t* f = move <= 2 ? fr : fc;
+            toggle(f, s1); toggle(f, s2);
+        } else if (move == 5) {
+            toggle(fr, s1);
+        } else if (move == 6) {
+            toggle(fc, s1);
+        } else if (move == 7) {                        // dissipator: an empty site is excited with probability 1/10
+            const bool r_empty = a.hilb == NQ_FOCK && get_bit(rb, s1) == 0;
+            const bool c_empty = a.hilb == NQ_FOCK && get_bit(cb, s1) == 0;
+            if (!r_empty || pick(d[2], 10) == 0) toggle(fr, s1);
+            if (!c_empty || pick(d[3], 10) == 0) toggle(fc, s1);
+        } else {                                       // jumper
+            toggle(fr, s1);
+            toggle(fc, pick(d[2], N));
+        }
+    } else {                                           // NQ_RULE_OPERATOR
+        const int nf = op_count(op, rb, DOUBLED ? cb : nullptr);
+        const int k = replay ? (int)(((uint64_t)d[0] * (uint64_t)nf) >> 32) : (int)(((uint64_t)d[0] * (uint64_t)nf) >> 32);
+        op_pick(op, rb, DOUBLED ? cb : nullptr, k, fr, fc);
+        uint64_t nr[MAXW], nc[MAXW];
+#pragma unroll
+        for (int w = 0; w < MAXW; w++) { nr[w] = rb[w] ^ fr[w]; nc[w] = DOUBLED ? cb[w] ^ fc[w] : 0ull; }
+        const int nb = op_count(op, nr, DOUBLED ? nc : nullptr);
+        p.bias = log((double)nf / (double)nb);
+    }
+    p.n = 0;
+    for (int w = 0; w < W64; w++) {
+        uint64_t m = fr[w];
+        while (m && p.n < MAXFLIP) { int b = __ffsll((long long)m) - 1; m &= m - 1; p.idx[p.n++] = w * 64 + b; }
+        m = DOUBLED ? fc[w] : 0ull;
+        while (m && p.n < MAXFLIP) { int b = __ffsll((long long)m) - 1; m &= m - 1; p.idx[p.n++] = N + w * 64 + b; }
+    }
+}
+
+template <typename E, int KIND, int ACT>
+__global__ void sampler_rule_kernel(const E* __restrict__ par, OpDev op, uint64_t* __restrict__ st_row,
+                                    uint64_t* __restrict__ st_col, RunArgs a) {
+    typedef typename elem_traits<E>::real T;
+    constexpr bool DOUBLED = KIND != NQ_RBM;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int64_t chain = blockIdx.x * (int64_t)wpb + warp;
+    if (chain >= a.B) return;
+    const int N = a.N, W64 = (N + 63) >> 6;
+    Units<E, KIND> un{par, N, a.M, a.A};
+    const int U = un.count();
+    // per warp: theta[2][U] (current / tentative), fval[2][U]
+    cxd* th = (cxd*)smem_raw + (size_t)warp * 3 * U;
+    double* fv = (double*)(th + 2 * U);
+    int cur = 0;
+    uint64_t rb[MAXW], cb[MAXW];
+#pragma unroll
+    for (int w = 0; w < MAXW; w++) {
+        rb[w] = w < W64 ? st_row[chain * W64 + w] : 0ull;
+        cb[w] = (DOUBLED && w < W64) ? st_col[chain * W64 + w] : 0ull;
+    }
+    unsigned nacc = 0;
+    const int nsteps = a.burn + a.L;
+    const uint64_t gid = (uint64_t)(a.chain_offset + chain);
+    for (int step = 0; step < nsteps; step++) {
+        for (int k = lane; k < U; k += 32) {
+            cxd t = un.bias(k);
+            for (int j = 0; j < N; j++) {
+                t += rscale((double)digit_value<T>(a.hilb, get_bit(rb, j)), un.slope(k, 0, j));
+                if (DOUBLED) t += rscale((double)digit_value<T>(a.hilb, get_bit(cb, j)), un.slope(k, 1, j));
+            }
+            th[cur * U + k] = t;
+            fv[cur * U + k] = un.weight(k) * unit_value<ACT>(t, KIND == NQ_NDM && k < 2 * a.M);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int ps = 0; ps < a.passes; ps++) {
+            const int pic = step * a.passes + ps;
+            uint32_t d[4];
+            T u;
+            if (a.replay) {
+                const int32_t* dr = a.draws + ((int64_t)pic * a.B + chain) * 4;
+                d[0] = (uint32_t)dr[0]; d[1] = (uint32_t)dr[1]; d[2] = (uint32_t)dr[2]; d[3] = (uint32_t)dr[3];
+                u = ((const T*)a.uniforms)[(int64_t)pic * a.B + chain];
+            } else {
+                const uint64_t pidx = a.pass_base + (uint64_t)pic;
+                Philox ph{(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+                uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)pidx, (uint32_t)(pidx >> 32)};
+                ph.gen(c);
+                u = uniform01<T>(c[1], c[2]);
+                Philox pr{(uint32_t)a.seed ^ 0x52554c45u /* "RULE" domain */, (uint32_t)(a.seed >> 32)};
+                uint32_t e[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)pidx, (uint32_t)(pidx >> 32)};
+                pr.gen(e);
+                d[0] = e[0]; d[1] = e[1]; d[2] = e[2]; d[3] = e[3];
+            }
+            Proposal p;
+            make_proposal<DOUBLED>(a, op, a.replay != 0, d, rb, cb, p);
+            // change of the site values and of the linear term
+            double dvs[MAXFLIP];
+            double dlp = 0.0;
+            for (int i = 0; i < p.n; i++) {
+                const int side = p.idx[i] >= N ? 1 : 0, j = p.idx[i] - side * N;
+                dvs[i] = (double)flip_delta<T>(a.hilb, get_bit(side ? cb : rb, j));
+                dlp += dvs[i] * un.lin_slope(side, j);
+            }
+            const int nxt = cur ^ 1;
+            double acc_sum = 0.0;
+            if (p.n > 0) {
+                for (int k = lane; k < U; k += 32) {
+                    cxd t = th[cur * U + k];
+                    for (int i = 0; i < p.n; i++) {
+                        const int side = p.idx[i] >= N ? 1 : 0, j = p.idx[i] - side * N;
+                        t += rscale(dvs[i], un.slope(k, side, j));
+                    }
+                    const double f = un.weight(k) * unit_value<ACT>(t, KIND == NQ_NDM && k < 2 * a.M);
+                    acc_sum += f - fv[cur * U + k];
+                    th[nxt * U + k] = t; fv[nxt * U + k] = f;
+                }
+                acc_sum = warp_sum(acc_sum);
+            }
+            const double pr_ratio = exp(acc_sum + dlp + p.bias);
+            const bool acc = (u - (T)pr_ratio) < T(0);
+            if (acc) {
+                if (p.n > 0) cur = nxt;
+                for (int i = 0; i < p.n; i++) {
+                    const int side = p.idx[i] >= N ? 1 : 0, j = p.idx[i] - side * N;
+                    toggle(side ? cb : rb, j);
+                }
+                nacc++;
+            }
+            __syncwarp();
+            if (a.replay && a.accept_out && lane == 0) a.accept_out[(int64_t)pic * a.B + chain] = acc ? 1 : 0;
+        }
+        if (step >= a.burn && a.out_prow && lane == 0) {
+            int64_t o = ((int64_t)(step - a.burn) * a.B + chain) * W64;
+            for (int w = 0; w < W64; w++) { a.out_prow[o + w] = rb[w]; if (DOUBLED && a.out_pcol) a.out_pcol[o + w] = cb[w]; }
+        }
+    }
+    if (lane == 0) {
+        for (int w = 0; w < W64; w++) { st_row[chain * W64 + w] = rb[w]; if (DOUBLED) st_col[chain * W64 + w] = cb[w]; }
+        if (nacc) atomicAdd(a.accepted, (unsigned long long)nacc);
+    }
+}
+
+template <typename E, int KIND, int ACT>
+int launch_sampler_rule(nq_sampler_t s, const RunArgs& a) {
+    nq_machine_t m = s->m;
+    nq_ctx_t ctx = m->ctx;
+    const int U = KIND == NQ_NDM ? 2 * m->M + m->A : m->M;
+    const size_t per_warp = (size_t)3 * U * sizeof(cxd);
+    int wpb = 4;
+    while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
+    const size_t smem = per_warp * wpb;
+    if (smem > ctx->smem_optin) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "sampler needs %zu B shared memory per chain", per_warp);
+    OpDev op;
+    memset(&op, 0, sizeof op);
+    if (s->rule == NQ_RULE_OPERATOR) op = op_dev(s->rule_op);
+    auto kern = sampler_rule_kernel<E, KIND, ACT>;
+    NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = (unsigned)((s->B + wpb - 1) / wpb);
+    NQ_LAUNCH(ctx, kern, grid, wpb * 32, smem, (const E*)m->params, op, s->prow, s->pcol, a);
+    return NQ_OK;
+}
+
+template <typename E>
+int dispatch_sampler_rule(nq_sampler_t s, const RunArgs& a) {
+    nq_machine_t m = s->m;
+    if (m->kind == NQ_RBMSPLIT) return launch_sampler_rule<E, NQ_RBMSPLIT, NQ_SOFTPLUS>(s, a);
+    if (m->kind == NQ_RBM)
+        return m->act == NQ_SOFTPLUS ? launch_sampler_rule<E, NQ_RBM, NQ_SOFTPLUS>(s, a) : launch_sampler_rule<E, NQ_RBM, NQ_LOGCOSH>(s, a);
+    return nq_fail(m->ctx, NQ_ERR_ARG, "machine kind / dtype mismatch");
+}
+
+int run_sampler_rule(nq_sampler_t s, const RunArgs& a) {
+    nq_machine_t m = s->m;
+    if (m->kind == NQ_NDM) {
+        if (m->dtype == NQ_F64)
+            return m->act == NQ_SOFTPLUS ? launch_sampler_rule<double, NQ_NDM, NQ_SOFTPLUS>(s, a) : launch_sampler_rule<double, NQ_NDM, NQ_LOGCOSH>(s, a);
+        return m->act == NQ_SOFTPLUS ? launch_sampler_rule<float, NQ_NDM, NQ_SOFTPLUS>(s, a) : launch_sampler_rule<float, NQ_NDM, NQ_LOGCOSH>(s, a);
+    }
+    switch (m->dtype) {
+        case NQ_F32: return dispatch_sampler_rule<float>(s, a);
+        case NQ_F64: return dispatch_sampler_rule<double>(s, a);
+        case NQ_C64: return dispatch_sampler_rule<cxf>(s, a);
+        default: return dispatch_sampler_rule<cxd>(s, a);
+    }
+}
+
 template <typename E, int ACT, bool DOUBLED>
 int launch_sampler_rbm(nq_sampler_t s, const RunArgs& a) {
     nq_machine_t m = s->m;
@@ -396,6 +695,10 @@ int dispatch_sampler_rbm(nq_sampler_t s, const RunArgs& a) {
 int run_sampler(nq_sampler_t s, const RunArgs& a) {
     nq_machine_t m = s->m;
     if (m->N > 64 * MAXW) return nq_fail(m->ctx, NQ_ERR_UNSUPPORTED, "sampler supports N <= %d", 64 * MAXW);
+    if (s->rule != NQ_RULE_LOCAL) {
+        if (s->diag) return nq_fail(m->ctx, NQ_ERR_UNSUPPORTED, "the diagonal chain uses LocalRule");
+        return run_sampler_rule(s, a);
+    }
     NQ_CHECK(nq_machine_ensure_tables(m));
     if (m->kind == NQ_NDM) {
         if (m->dtype == NQ_F64)
@@ -417,6 +720,7 @@ RunArgs base_args(nq_sampler_t s) {
     a.B = s->B; a.N = m->N; a.M = m->M; a.A = m->A; a.hilb = (int)m->hilb; a.passes = s->passes;
     a.seed = s->seed; a.pass_base = s->pass_base; a.chain_offset = s->chain_offset; a.accepted = s->accepted;
     a.diag = s->diag;
+    a.rule = s->rule; a.n_coup = s->n_coup; a.coup = s->coup;
     return a;
 }
 
@@ -434,6 +738,7 @@ extern "C" int nq_sampler_create(nq_machine_t m, int64_t B, int passes, uint64_t
     s->passes = (passes % 2 == 0) ? passes + 1 : passes;   // Metropolis.jl:30-38
     s->seed = seed; s->chain_offset = chain_offset; s->pass_base = 0; s->passes_done = 0; s->diag = 0;
     s->prow = s->pcol = nullptr; s->accepted = nullptr;
+    s->rule = NQ_RULE_LOCAL; s->n_coup = 0; s->coup = nullptr; s->rule_op = nullptr;
     size_t pbytes = (size_t)B * nq_words(m->N) * 8;
     bool ok = cudaMalloc((void**)&s->prow, pbytes) == cudaSuccess &&
               (!m->doubled() || cudaMalloc((void**)&s->pcol, pbytes) == cudaSuccess) &&
@@ -455,9 +760,65 @@ extern "C" int nq_sampler_destroy(nq_sampler_t s) {
     if (!s) return NQ_ERR_ARG;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
-    cudaFree(s->prow); cudaFree(s->pcol); cudaFree(s->accepted);
+    cudaFree(s->prow); cudaFree(s->pcol); cudaFree(s->accepted); cudaFree(s->coup);
     delete s;
     return NQ_OK;
+}
+
+extern "C" int nq_sampler_set_rule(nq_sampler_t s, nq_rule rule, int n_couplings, const int32_t* couplings, nq_operator_t op) {
+    if (!s) return NQ_ERR_ARG;
+    nq_machine_t m = s->m;
+    nq_ctx_t ctx = m->ctx;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (rule == NQ_RULE_EXCHANGE) {
+        if (m->doubled()) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "ExchangeRule is defined for ket states (ExchangeRule.jl:46-48)");
+        if (n_couplings <= 0 || !couplings) return nq_fail(ctx, NQ_ERR_ARG, "ExchangeRule needs at least one coupling");
+    } else if (rule == NQ_RULE_NAGY) {
+        if (!m->doubled()) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "NagyRule is defined for doubled states (Nagy.jl:40)");
+        // adjacency_list[site] indexes the list of couples by SITE number (Nagy.jl:51): fewer couples than sites is a
+        // BoundsError in the reference
+        if (n_couplings < m->N || !couplings) return nq_fail(ctx, NQ_ERR_ARG, "NagyRule indexes its couplings by site: %d couplings < %d sites", n_couplings, m->N);
+    } else if (rule == NQ_RULE_OPERATOR) {
+        if (!op) return nq_fail(ctx, NQ_ERR_ARG, "OperatorRule needs an operator");
+        if (op->N != m->N || (op->space == NQ_SUPER) != m->doubled())
+            return nq_fail(ctx, NQ_ERR_SHAPE, "OperatorRule: the operator does not act on the machine's space");
+        if (op->max_part_sites > MAXFLIP / 2) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "OperatorRule: parts of more than %d sites", MAXFLIP / 2);
+    } else if (rule != NQ_RULE_LOCAL) {
+        return nq_fail(ctx, NQ_ERR_ARG, "unknown rule %d", (int)rule);
+    }
+    if (rule == NQ_RULE_EXCHANGE || rule == NQ_RULE_NAGY) {
+        std::vector<int32_t> h(2 * (size_t)n_couplings);
+        NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (nq_is_device_ptr(couplings)) NQ_CUDA(ctx, cudaMemcpy(h.data(), couplings, h.size() * 4, cudaMemcpyDeviceToHost));
+        else memcpy(h.data(), couplings, h.size() * 4);
+        for (int32_t v : h) if (v < 0 || v >= m->N) return nq_fail(ctx, NQ_ERR_ARG, "coupling site %d outside 0..%d", (int)v, m->N - 1);
+        cudaFree(s->coup); s->coup = nullptr;
+        NQ_CUDA(ctx, cudaMalloc((void**)&s->coup, h.size() * 4));
+        NQ_CUDA(ctx, cudaMemcpy(s->coup, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+        s->n_coup = n_couplings;
+    }
+    s->rule = (int)rule;
+    s->rule_op = rule == NQ_RULE_OPERATOR ? op : nullptr;
+    return NQ_OK;
+}
+
+extern "C" int nq_sampler_replay_rule(nq_sampler_t s, const int32_t* draws, const void* uniforms, uint8_t* accept_out) {
+    if (!s || !draws || !uniforms) return NQ_ERR_ARG;
+    nq_machine_t m = s->m;
+    nq_ctx_t ctx = m->ctx;
+    if (s->rule == NQ_RULE_LOCAL) return nq_fail(ctx, NQ_ERR_ARG, "LocalRule replays through nq_sampler_replay");
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    NqStage st(ctx);
+    size_t n = (size_t)s->passes * s->B;
+    RunArgs a = base_args(s);
+    a.replay = 1; a.burn = 0; a.L = 1;
+    a.draws = (const int32_t*)st.in(SL_IN0, draws, n * 16);
+    a.uniforms = st.in(SL_IN1, uniforms, n * nq_dtype_size(nq_real_of(m->dtype)));
+    a.accept_out = accept_out ? (uint8_t*)st.out(SL_OUT0, accept_out, n) : nullptr;
+    if (st.status != NQ_OK) return st.status;
+    NQ_CHECK(run_sampler(s, a));
+    s->passes_done += (int64_t)n;
+    return st.finish();
 }
 
 extern "C" int nq_sampler_set_state(nq_sampler_t s, const void* srow, const void* scol, nq_dtype sdtype) {

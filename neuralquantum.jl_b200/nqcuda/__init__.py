@@ -7,8 +7,9 @@ from ._lib import NQError, PosDefException, NotConvergedError, EXPORTS, LIB_PATH
 from .core import Context, HomogeneousSpin, HomogeneousFock, Hilbert, unique_id
 from .operators import (LocalOperator as _LocalOperator, KLocalOperatorRow, Liouvillian, liouvillian, sigmax, sigmay,
                         sigmaz, sigmam, sigmap, destroy, create, number, DeviceOperator)
-from .machines import RBM, RBMSplit, NDM, af_softplus, af_logcosh, init_random_pars_
-from .samplers import MetropolisSampler, MetropolisSamplerCache, LocalRule, ExactSampler, ExactSamplerCache
+from .machines import RBM, RBMSplit, NDM, NDMSymm, symmetry_maps, af_softplus, af_logcosh, init_random_pars_, ket, densitymatrix
+from .samplers import (MetropolisSampler, MetropolisSamplerCache, LocalRule, ExchangeRule, NagyRule, OperatorRule, ExactSampler,
+                       ExactSamplerCache)
 from .algorithms import (SR, Descent, Nesterov, update_, local_scalar, local_grad, stat_analysis, Measurement, sr_cholesky,
                          sr_cg, sr_minres, sr_qlp, sr_shift, sr_multiplicative, sr_none)
 from .iterative import BatchedSampler, BatchedObsDMSampler

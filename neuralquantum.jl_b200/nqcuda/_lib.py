@@ -22,6 +22,7 @@ NQ_F32, NQ_F64, NQ_C64, NQ_C128 = 0, 1, 2, 3
 NQ_SPIN, NQ_FOCK = 0, 1
 NQ_KET, NQ_SUPER = 0, 1
 NQ_SOLVE_CHOLESKY, NQ_SOLVE_CG, NQ_SOLVE_MINRES, NQ_SOLVE_QLP, NQ_SOLVE_QLP_WARM = 0, 1, 2, 3, 4
+NQ_RULE_LOCAL, NQ_RULE_EXCHANGE, NQ_RULE_NAGY, NQ_RULE_OPERATOR = 0, 1, 2, 3
 NQ_UNIQUE_ID_BYTES = 128
 
 NP_OF = {NQ_F32: np.float32, NQ_F64: np.float64, NQ_C64: np.complex64, NQ_C128: np.complex128}
@@ -102,7 +103,20 @@ _PROTOS = {
     "nq_sampler_set_mode": (_i32, [_vp, _i32]),
     "nq_sampler_replay": (_i32, [_vp, _vp, _vp, _vp]),
     "nq_sampler_sample": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32]),
+    "nq_sampler_set_rule": (_i32, [_vp, _i32, _i32, _vp, _vp]),
+    "nq_sampler_replay_rule": (_i32, [_vp, _vp, _vp, _vp]),
     "nq_sampler_counters": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "nq_symm_create": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, C.POINTER(_vp)]),
+    "nq_symm_destroy": (_i32, [_vp]),
+    "nq_symm_nparams": (_i32, [_vp, C.POINTER(_i64)]),
+    "nq_symm_set_params": (_i32, [_vp, _vp, _i64]),
+    "nq_symm_get_params": (_i32, [_vp, _vp, _i64]),
+    "nq_symm_update": (_i32, [_vp, _vp, _dbl]),
+    "nq_symm_gradient": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _i64]),
+    "nq_fullspace_size": (_i32, [_vp, C.POINTER(_i64)]),
+    "nq_fullspace_state": (_i32, [_vp, _i32, _vp]),
+    "nq_exact_table": (_i32, [_vp, _vp]),
+    "nq_exact_sample": (_i32, [_vp, _vp, _u64, _i64, _u64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "nq_center": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "nq_force_ket": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),
     "nq_force_liouvillian": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, C.POINTER(_dbl)]),

@@ -27,9 +27,14 @@ def local_grad(net, op, sigma):
     """(L_loc [B], grad L_loc [P, B]) for a Liouvillian (AccumulatorObsGrad semantics)."""
     sr, sc, B = net._states(sigma)
     out = np.zeros(B, dtype=net.cdtype)
-    g = np.zeros((net.P, B), dtype=net.cdtype, order="F")
+    Pk = getattr(net, "Pb", net.P)                   # symmetrised machines: the kernel writes rows of the bare net
+    g = np.zeros((Pk, B), dtype=net.cdtype, order="F")
     L.check(L.lib.nq_local_grad(net.h, op.h, L.ptr(sr), L.ptr(sc), L.nq_dtype(sr.dtype), B, None, L.ptr(out), L.ptr(g),
-                                net.P), net.ctx.h)
+                                Pk), net.ctx.h)
+    if Pk != net.P:
+        gs = np.zeros((net.P, B), dtype=net.cdtype, order="F")
+        net.symmetrize(L.ptr(g), Pk, B, L.ptr(gs), net.P)
+        g = gs
     return out, g
 
 

@@ -74,6 +74,11 @@ class BatchedSampler:
         self.O = torch.zeros((Ns, P), dtype=ot, device=dev)            # = [P, Ns] column-major
         self.loc = torch.zeros(Ns, dtype=ct, device=dev)
         self.gloc = torch.zeros((Ns, P), dtype=ct, device=dev) if self.is_liouvillian else None
+        # symmetrised machines (NDMSymm): the kernels write rows of the BARE net, symmetrised into O / gloc afterwards
+        self.symm = hasattr(net, "bare")
+        if self.symm:
+            self.O_bare = torch.zeros((Ns, net.Pb), dtype=ot, device=dev)
+            self.gloc_bare = torch.zeros((Ns, net.Pb), dtype=ct, device=dev) if self.is_liouvillian else None
         self.avg = torch.zeros(P, dtype=ot, device=dev)
         self.gradC = torch.zeros(P, dtype=ct, device=dev)
         self.real_params = net.real_params
@@ -114,6 +119,14 @@ class BatchedSampler:
         net, ctx, Ns = self.net, self.ctx, self.Ns
         pc = self.pcol.data_ptr() if self.pcol is not None else None
         gl = self.gloc.data_ptr() if self.is_liouvillian else None
+        if self.symm:       # logpsi_and_grad!(::NDMSymm): bare rows, then symmetrize_grad_NDM_batched! (NDMSymmBatched.jl:16-36)
+            glb = self.gloc_bare.data_ptr() if self.is_liouvillian else None
+            L.check(L.lib.nq_logpsi_grad_local_packed(net.h, self.op.h, self.prow.data_ptr(), pc, Ns, self.logpsi.data_ptr(),
+                                                      self.O_bare.data_ptr(), net.Pb, self.loc.data_ptr(), glb, net.Pb), ctx.h)
+            net.symmetrize(self.O_bare.data_ptr(), net.Pb, Ns, self.O.data_ptr(), net.P)
+            if self.is_liouvillian:
+                net.symmetrize(glb, net.Pb, Ns, gl, net.P)
+            return
         L.check(L.lib.nq_logpsi_grad_local_packed(net.h, self.op.h, self.prow.data_ptr(), pc, Ns, self.logpsi.data_ptr(),
                                                   self.O.data_ptr(), net.P, self.loc.data_ptr(), gl, net.P), ctx.h)
 
@@ -248,6 +261,9 @@ class BatchedSampler:
             if delta.dtype != _tdtype(net.dtype):
                 delta = delta.to(_tdtype(net.dtype))
             delta = delta.contiguous()
+        if self.symm:
+            L.check(L.lib.nq_symm_update(net.g, delta.data_ptr(), float(eta)), self.ctx.h)
+            return
         L.check(L.lib.nq_update(net.h, delta.data_ptr(), float(eta)), self.ctx.h)
 
 

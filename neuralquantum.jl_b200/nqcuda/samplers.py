@@ -12,14 +12,60 @@ from . import _lib as L
 
 class LocalRule:
     """Transition rule: flip one random site (LocalRule.jl:10-28)."""
+    code = L.NQ_RULE_LOCAL
+
+
+def _couplings(op):
+    """The site pairs of the 2-site terms of an operator, in term order (ExchangeRule.jl:17-34); 3-site couplings are
+    ignored with a warning like the reference."""
+    import warnings
+    out = []
+    for t in op.terms:
+        if len(t.sites) == 1:
+            continue
+        if len(t.sites) > 2:
+            warnings.warn("Can't exchange between 3-site couplings. This coupling is ignored")
+            continue
+        out.append((int(t.sites[0]), int(t.sites[1])))
+    return out
+
+
+class ExchangeRule:
+    """ExchangeRule(H): at every step a random couple of sites coupled by a 2-body term of H is switched
+    (ExchangeRule.jl:3-34).  `distances` = list of 1-based site pairs.  Ket states only, like the reference."""
+    code = L.NQ_RULE_EXCHANGE
+
+    def __init__(self, graph):
+        self.distances = list(graph) if isinstance(graph, (list, tuple)) else _couplings(graph)
+        if not self.distances:
+            raise ValueError("ExchangeRule: the operator has no 2-site couplings")
+
+
+class NagyRule:
+    """NagyRule(H): the 8 moves of Nagy.jl:40-115 on doubled states (hopping in sigma / sigma', single flips, the
+    dissipator move, the jumper).  `adjacency_list` is the list of 2-site couplings; the reference indexes it by SITE
+    number (Nagy.jl:51), so it needs at least nsites entries."""
+    code = L.NQ_RULE_NAGY
+
+    def __init__(self, graph):
+        self.adjacency_list = list(graph) if isinstance(graph, (list, tuple)) else _couplings(graph)
+
+
+class OperatorRule:
+    """OperatorRule(O): a move is drawn uniformly from the connections of O; log_prob_bias = log(n_forward / n_back)
+    (OperatorRule.jl:3-59)."""
+    code = L.NQ_RULE_OPERATOR
+
+    def __init__(self, operator):
+        self.operator = operator
 
 
 class MetropolisSampler:
     """MetropolisSampler(rule, chain_length, passes; burn=0, seed).  Even `passes` is bumped to odd."""
 
     def __init__(self, rule, chain_length, passes, burn=0, seed=None):
-        if not isinstance(rule, LocalRule):
-            raise NotImplementedError("the device sampler implements LocalRule (north_star scope)")
+        if not isinstance(rule, (LocalRule, ExchangeRule, NagyRule, OperatorRule)):
+            raise TypeError("unknown transition rule %r" % (rule,))
         assert passes > 0 and chain_length > 0
         self.rule, self.chain_length, self.burn_length = rule, int(chain_length), int(burn)
         self.passes = passes + 1 if passes % 2 == 0 else passes
@@ -37,6 +83,26 @@ class MetropolisSamplerCache:
         L.check(L.lib.nq_sampler_create(net.h, self.B, sampler.passes, sampler.seed, int(chain_offset), C.byref(h)),
                 net.ctx.h)
         self.h = h
+        rule = sampler.rule
+        if not isinstance(rule, LocalRule):
+            coup, op, n = None, None, 0
+            if isinstance(rule, (ExchangeRule, NagyRule)):
+                pairs = rule.distances if isinstance(rule, ExchangeRule) else rule.adjacency_list
+                coup = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2) - 1)     # 0-based
+                n = coup.shape[0]
+            else:
+                self._rule_op = rule.operator.to_device(net.ctx)       # kept alive with the chain
+                op = self._rule_op.h
+            L.check(L.lib.nq_sampler_set_rule(h, rule.code, n, L.ptr(coup), op), net.ctx.h)
+
+    def replay_rule(self, draws, uniforms):
+        """One samplenext! of a non-local rule with supplied randomness: draws [passes, B, 4] (the integers the reference
+        draws, see nq_sampler_replay_rule), uniforms [passes, B]."""
+        draws = np.ascontiguousarray(draws, dtype=np.int64).astype(np.uint32).view(np.int32).reshape(self.s.passes, self.B, 4)
+        uniforms = np.ascontiguousarray(uniforms, dtype=self.net.rdtype)
+        acc = np.zeros((self.s.passes, self.B), dtype=np.uint8)
+        L.check(L.lib.nq_sampler_replay_rule(self.h, L.ptr(draws), L.ptr(uniforms), L.ptr(acc)), self.net.ctx.h)
+        return acc.astype(bool)
 
     def __del__(self):
         try:
@@ -105,52 +171,40 @@ class ExactSampler:
 
 
 class ExactSamplerCache:
-    """Exact.jl:135-181 on the device: log-probabilities of ALL basis states through the machine kernel (packed
-    index = basis number: site 1 is the least significant digit, super-index = col * D + row), a cumulative table,
-    and one independent inverse-CDF draw per (chain, slot).  The table and the draws use torch ops: this is the
-    reference's validation sampler, not part of the hot path.  Julia's MersenneTwister stream is not reproduced."""
+    """Exact.jl:135-181 on the device (csrc/nq_fullspace.cu): log-probabilities of ALL basis states through the machine
+    kernel (basis number = packed digits, site 1 least significant; super-index = col * D + row), a cumulative table
+    built by a deterministic device scan (nq_exact_table), and one inverse-CDF draw per (slot, chain) with Philox
+    uniforms keyed by the global chain id (nq_exact_sample).  Julia's MersenneTwister stream is not reproduced; replay
+    with supplied uniforms gives the reference's searchsortedfirst indices bit for bit."""
     MAX_TABLE = 1 << 24
 
     def __init__(self, sampler, net, batch_sz, chain_offset=0, num_workers=1):
         import torch
-        if net.N > 62:
-            raise ValueError("ExactSampler needs an indexable space")
         self.s, self.net, self.B = sampler, net, int(batch_sz)
         self.loc_chain_length = -(-sampler.samples_length // num_workers)            # Exact.jl:41
+        self.chain_offset = int(chain_offset)
+        size = C.c_int64()
+        L.check(L.lib.nq_fullspace_size(net.h, C.byref(size)), net.ctx.h)
+        self.size = size.value
         self.D = 1 << net.N
-        self.size = self.D * self.D if net.doubled else self.D
         if self.size > self.MAX_TABLE:
-            raise ValueError("ExactSampler: %d table entries (Closed N < 24, Open N < 12)" % self.size)
-        self.gen = torch.Generator(device=torch.device("cuda", net.ctx.device))
-        self.gen.manual_seed((sampler.seed + 0x9E3779B97F4A7C15 * (chain_offset + 1)) % (1 << 63))
-        self.cdf = None
+            raise ValueError("ExactSampler: %d table entries (Closed N <= 24, Open N <= 12)" % self.size)
+        self.cdf = torch.zeros(self.size, dtype=torch.float64, device=torch.device("cuda", net.ctx.device))
+        self.draws = 0
+        self.valid = False
 
     def init_sampler(self):
         """init_sampler!: the probability table of the CURRENT parameters."""
-        import torch
-        net, dev = self.net, torch.device("cuda", self.net.ctx.device)
-        idx = torch.arange(self.size, dtype=torch.int64, device=dev)
-        row = (idx % self.D).contiguous() if net.doubled else idx
-        col = (idx // self.D).contiguous() if net.doubled else None
-        from .iterative import _tdtype
-        out = torch.zeros(self.size, dtype=_tdtype(net.out_dtype), device=dev)
-        L.check(L.lib.nq_logpsi_packed(net.h, row.data_ptr(), col.data_ptr() if col is not None else None, self.size,
-                                       out.data_ptr()), net.ctx.h)
-        lp = 2.0 * out.real.to(torch.float64) if out.is_complex() else 2.0 * out.to(torch.float64)   # log_prob_psi
-        p = torch.exp(lp - lp.max())
-        self.cdf = torch.cumsum(p, 0)
-        self.cdf /= self.cdf[-1].clone()
+        L.check(L.lib.nq_exact_table(self.net.h, self.cdf.data_ptr()), self.net.ctx.h)
+        self.valid = True
         return self.cdf
 
-    def sample_into(self, L_store, prow, pcol):
-        """samplenext! for every (slot, chain): basis number by inverse CDF, written as packed words [L, B, 1]."""
-        import torch
+    def sample_into(self, L_store, prow, pcol, uniforms=None, indices=None):
+        """samplenext! for every (slot, chain): packed words [L, B, 1] on the device; `uniforms` [L, B] replays."""
         self.init_sampler()
-        u = torch.rand((L_store, self.B), generator=self.gen, device=self.cdf.device, dtype=torch.float64)
-        hi = torch.searchsorted(self.cdf, u.reshape(-1)).clamp_(max=self.size - 1).reshape(L_store, self.B)
-        if self.net.doubled:
-            prow[:, :, 0] = hi % self.D
-            pcol[:, :, 0] = hi // self.D
-        else:
-            prow[:, :, 0] = hi
-        return hi
+        u = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64)
+        L.check(L.lib.nq_exact_sample(self.net.h, self.cdf.data_ptr(), self.s.seed, self.chain_offset, self.draws,
+                                      self.B, int(L_store), L.ptr(u), L.ptr(prow), L.ptr(pcol), L.ptr(indices)),
+                self.net.ctx.h)
+        if uniforms is None:
+            self.draws += int(L_store)

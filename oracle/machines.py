@@ -257,3 +257,98 @@ def random_machine(kind, N, alpha, *, act=SOFTPLUS, complex_weights=False, seed=
         A = int((alpha if alpha_a is None else alpha_a) * N)
         return NDM(rn(N), rn(M), rn(M, N), rn(A, N), rn(N), rn(M), rn(A), rn(M, N), rn(A, N), act)
     raise ValueError(kind)
+
+
+# ----- NDMSymm --------------------------------------------------------------------------
+class NDMSymm:
+    """NDMSymm.jl:3-25: a symmetric NDM (alpha_h, alpha_a FEATURES) expanded into a bare NDM with alpha * n_symm units
+    by the site permutations; gradients of the bare net are multiplied by the dense 0/1 matrices of
+    construct_grad_matrices (NDMSymm.jl:130-181, ones/n for the local biases), field by field
+    (symmetrize_grad_NDM!, NDMSymm.jl:65-76).  `permutations`: n_symm lists of N 1-based sites."""
+    kind = "ndmsymm"
+    doubled = True
+    is_complex = False
+
+    def __init__(self, symm_net, permutations):
+        self.symm = symm_net
+        self.perms = [list(p) for p in permutations]
+        ns, N = len(self.perms), symm_net.N
+        Ms, As = symm_net.M, symm_net.A
+        z = np.zeros
+        self.bare = NDM(z(N), z(Ms * ns), z((Ms * ns, N)), z((As * ns, N)), z(N), z(Ms * ns), z(As * ns), z((Ms * ns, N)),
+                        z((As * ns, N)), symm_net.act)
+        self.N, self.act = N, symm_net.act
+        self._matrices()
+        self.set_bare_params()
+
+    @property
+    def P(self):
+        return self.symm.P
+
+    def params(self):
+        return self.symm.params()
+
+    def set_params(self, w):
+        self.symm.set_params(w)
+        self.set_bare_params()
+
+    def set_bare_params(self):                          # NDMSymm.jl:79-128
+        s, b, ns = self.symm, self.bare, len(self.perms)
+        s.b_mu = np.full_like(s.b_mu, s.b_mu.sum() / len(s.b_mu))
+        s.b_lam = np.full_like(s.b_lam, s.b_lam.sum() / len(s.b_lam))
+        b.b_mu, b.b_lam = s.b_mu.copy(), s.b_lam.copy()
+        for i in range(s.M):
+            b.h_mu[i * ns:(i + 1) * ns] = s.h_mu[i]
+            b.h_lam[i * ns:(i + 1) * ns] = s.h_lam[i]
+        for i in range(s.A):
+            b.d_lam[i * ns:(i + 1) * ns] = s.d_lam[i]
+        for f in range(s.M):
+            for j, perm in enumerate(self.perms):
+                for i, ip in enumerate(perm):
+                    b.w_mu[j + f * ns, ip - 1] = s.w_mu[f, i]
+                    b.w_lam[j + f * ns, ip - 1] = s.w_lam[f, i]
+        for f in range(s.A):
+            for j, perm in enumerate(self.perms):
+                for i, ip in enumerate(perm):
+                    b.u_mu[j + f * ns, ip - 1] = s.u_mu[f, i]
+                    b.u_lam[j + f * ns, ip - 1] = s.u_lam[f, i]
+
+    def _matrices(self):                                # NDMSymm.jl:130-181
+        s, ns, N = self.symm, len(self.perms), self.N
+        self.Gb = np.ones((N, N)) / N
+        self.Gh = np.zeros((s.M, s.M * ns))
+        for k in range(s.M):
+            self.Gh[k, k * ns:(k + 1) * ns] = 1
+        self.Gd = np.zeros((s.A, s.A * ns))
+        for k in range(s.A):
+            self.Gd[k, k * ns:(k + 1) * ns] = 1
+
+        def wmat(K):
+            G = np.zeros((K * N, K * ns * N))
+            for f in range(K):
+                for j, perm in enumerate(self.perms):
+                    for i, ip in enumerate(perm):
+                        G[f + K * i, (j + f * ns) + K * ns * (ip - 1)] = 1
+            return G
+        self.Gw, self.Gu = wmat(s.M), wmat(s.A)
+
+    def logpsi(self, sr, sc):
+        return self.bare.logpsi(sr, sc)
+
+    def logpsi_grad(self, sr, sc):                      # NDMSymmBatched.jl:16-36
+        out, Ob = self.bare.logpsi_grad(sr, sc)
+        N, Mb, Ab = self.N, self.bare.M, self.bare.A
+        sizes = [N, Mb, Mb * N, Ab * N, N, Mb, Ab, Mb * N, Ab * N]
+        mats = [self.Gb, self.Gh, self.Gw, self.Gu, self.Gb, self.Gh, self.Gd, self.Gw, self.Gu]
+        blocks, o = [], 0
+        for sz, G in zip(sizes, mats):
+            blocks.append(G @ Ob[o:o + sz])
+            o += sz
+        return out, np.concatenate(blocks, axis=0)
+
+
+def random_ndmsymm(N, alpha_h, alpha_a, permutations, act=SOFTPLUS, seed=1234, std=0.1):
+    rng = np.random.Generator(np.random.Philox(seed))
+    rn = lambda *shape: rng.standard_normal(shape) * std
+    Ms, As = alpha_h, alpha_a
+    return NDMSymm(NDM(rn(N), rn(Ms), rn(Ms, N), rn(As, N), rn(N), rn(Ms), rn(As), rn(Ms, N), rn(As, N), act), permutations)

@@ -26,7 +26,9 @@ for r in rows[2:]:
 base = ins[0][0]
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
-cub = glob.glob(os.path.join(tmp, "*.cubin"))[0]
+# a linked library holds one cubin per translation unit: take the one whose symbol table names the kernel
+cubs = sorted(glob.glob(os.path.join(tmp, "*.cubin")))
+cub = next((c for c in cubs if mangled.encode() in open(c, "rb").read()), cubs[0])
 dis = subprocess.run(["nvdisasm", "-gi" if outer else "-g", "-c", cub], capture_output=True, text=True).stdout.splitlines()
 line_of = {}
 cur, infunc = None, False
@@ -56,7 +58,8 @@ print("samples", tot_s, "warp-instr", tot_e, "instructions", len(ins))
 srcs = {}
 for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][1 if by_ins else 0])[:top]:
     if f not in srcs:
-        cand = glob.glob(os.path.join(os.path.dirname(os.path.abspath(obj)), "..", "csrc", f))
+        cand = (glob.glob(os.path.join(os.path.dirname(os.path.abspath(obj)), "..", "csrc", f)) +
+                glob.glob(os.path.join(os.path.dirname(os.path.abspath(obj)), "csrc", f)))
         srcs[f] = open(cand[0]).read().splitlines() if cand else []
     text = srcs[f][ln - 1].strip()[:80] if 0 < ln <= len(srcs[f]) else ""
     st = sorted(zip(a[2], [h[i][6:] for i in stall_cols]), reverse=True)[:2]

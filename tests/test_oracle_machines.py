@@ -134,3 +134,32 @@ def test_param_roundtrip_and_layout():
 def test_logcosh_large_argument_branch():
     x = np.array([-30.0, -12.0, 12.0, 13.0, 40.0])
     assert np.allclose(M.logcosh(x), np.abs(x) + np.log1p(np.exp(-2 * np.abs(x))) - np.log(2), atol=1e-9)
+
+
+def test_ndmsymm_gradient_is_the_derivative_in_the_symmetric_space():
+    """NDMSymm.jl:36-76: grad_symm = G grad_bare must be the derivative of log rho(bare(w_symm)) with respect to the
+    symmetric parameters (the local biases enter through their mean)."""
+    from oracle import machines as OM
+    N = 4
+    perms = [[(i + s) % N + 1 for i in range(N)] for s in range(N)]
+    net = OM.random_ndmsymm(N, 2, 1, perms, seed=5, std=0.3)
+    assert net.bare.M == 2 * N and net.bare.A == N
+    rng = np.random.default_rng(1)
+    sr = rng.integers(0, 2, size=(N, 5)).astype(float)
+    sc = rng.integers(0, 2, size=(N, 5)).astype(float)
+    out, O = net.logpsi_grad(sr, sc)
+    w0 = net.params().copy()
+    h = 1e-6
+    for p in rng.choice(net.P, size=12, replace=False):
+        wp, wm = w0.copy(), w0.copy()
+        wp[p] += h
+        wm[p] -= h
+        net.set_params(wp)
+        fp = net.logpsi(sr, sc)
+        net.set_params(wm)
+        fm = net.logpsi(sr, sc)
+        assert np.allclose((fp - fm) / (2 * h), O[p], atol=1e-7), p
+    net.set_params(w0)
+    # translation invariance of the symmetrised density matrix: rho(T sigma, T sigma') = rho(sigma, sigma')
+    shift = lambda a: np.roll(a, 1, axis=0)
+    assert np.allclose(net.logpsi(shift(sr), shift(sc)), net.logpsi(sr, sc), atol=1e-12)
