@@ -307,6 +307,20 @@ int nq_sr_solve_matfree(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, in
 int nq_sr_solve_matfree_algo(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total,
                              nq_dtype dtype, const void* F, int real_params, double eps, nq_solver algo, double tol,
                              int64_t maxiter, void* dw, int64_t* iters);
+/* Streaming S assembly for batches whose gradient matrix does not fit in memory (BASELINE cfg5): rows are produced chunk
+ * by chunk into one reused device buffer (nq_logpsi_grad_packed) and consumed at once.  O: UNCENTRED rows [P, Nc] of the
+ * chunk, OVERWRITTEN (shifted by a provisional mean, the mean of the first chunk); Sacc [P,P] (element type of S, see
+ * nq_sr_setup) accumulates the Gram matrix of the shifted rows / Ns_total; state [2 P] complex128 holds the running sums
+ * and the shift; first != 0 initialises both.  nq_sr_finish applies the rank-one correction (and all-reduces the partial
+ * sums under sharding): Sacc is then the S of nq_center + nq_sr_setup on the whole batch and state[0..P) = <O>.
+ * Device buffers only.
+ * ref: BaseIterativeSampler.jl:19-26 + SRDirect.jl:26-49 (the reference needs O of the whole batch in memory) */
+int nq_sr_accumulate(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, int64_t Nc, int64_t Ns_total, nq_dtype dtype,
+                     int real_params, void* Sacc, void* state, int first);
+int nq_sr_finish(nq_ctx_t ctx, void* Sacc, void* state, int64_t P, int64_t Ns_total, nq_dtype dtype, int real_params);
+/* Nesterov(lr, mu): d = mu^2 v - (1 + mu) lr dw; v <- mu v - lr dw; delta = -d (apply with nq_update(m, delta, 1)).
+ * velocity, dw, delta: device vectors of n elements of `dtype`.  ref: Optimisers/rules.jl:36-55 */
+int nq_nesterov(nq_ctx_t ctx, void* velocity, const void* dw, int64_t n, nq_dtype dtype, double lr, double mu, void* delta);
 /* w <- w - eta dw on the machine's device parameters.  dw has the machine dtype (real for NDM).
  * ref: Optimisers/rules.jl:11-17, apply.jl:25-73 */
 int nq_update(nq_machine_t m, const void* dw, double eta);

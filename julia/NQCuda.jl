@@ -427,4 +427,104 @@ function precondition!(g::CudaSRCache, algo::SR, iter_n)
     return g.Δw
 end
 
+# ---- transition rules other than LocalRule (MCMCRules/ExchangeRule.jl, Nagy.jl, OperatorRule.jl) --------------------
+const NQ_RULE_LOCAL, NQ_RULE_EXCHANGE, NQ_RULE_NAGY, NQ_RULE_OPERATOR = Cint.(0:3)
+couples(pairs) = Int32[x - 1 for p in pairs for x in p]                  # 1-based (i, j) tuples -> 0-based flat [n][2]
+function set_rule!(sc::CudaSamplerCache, r::NeuralQuantum.ExchangeRule)
+    cp = couples(r.distances)
+    check(sc.net.ctx, ccall((:nq_sampler_set_rule, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Cvoid}),
+                            sc.h, NQ_RULE_EXCHANGE, length(r.distances), cp, C_NULL))
+end
+function set_rule!(sc::CudaSamplerCache, r::NeuralQuantum.NagyRule)
+    cp = couples(r.adjacency_list)
+    check(sc.net.ctx, ccall((:nq_sampler_set_rule, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Cvoid}),
+                            sc.h, NQ_RULE_NAGY, length(r.adjacency_list), cp, C_NULL))
+end
+function set_rule!(sc::CudaSamplerCache, r::NeuralQuantum.OperatorRule, op::CudaOperator)
+    check(sc.net.ctx, ccall((:nq_sampler_set_rule, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Cvoid}),
+                            sc.h, NQ_RULE_OPERATOR, 0, C_NULL, op.h))
+end
+# draws [4, B, passes] Int32: the integers the rule draws per proposal (see nq_sampler_replay_rule)
+function samplenext_replay_rule!(sc::CudaSamplerCache, draws::Array{Int32,3}, uniforms::Matrix, accepted::Matrix{UInt8})
+    check(sc.net.ctx, ccall((:nq_sampler_replay_rule, lib), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Cvoid}, Ptr{UInt8}),
+                            sc.h, draws, uniforms, accepted))
+end
+
+# ---- full-space tools: ket / densitymatrix (utils/densitymatrix.jl:9-62), ExactSampler (Samplers/Exact.jl:135-181) ----
+function fullspace_size(c::CudaNet)
+    n = Ref{Int64}(0)
+    check(c.ctx, ccall((:nq_fullspace_size, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}), c.h, n))
+    return Int(n[])
+end
+function NeuralQuantum.ket(c::CudaNet{<:RBM}, hilb, norm = true)
+    ψ = zeros(out_type(c.net), fullspace_size(c))
+    check(c.ctx, ccall((:nq_fullspace_state, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), c.h, norm ? 1 : 0, ψ))
+    return ψ
+end
+function NeuralQuantum.densitymatrix(c::CudaNet{<:Union{RBMSplit,NDM}}, hilb, norm = true)
+    D = 1 << NeuralQuantum.nsites(NeuralQuantum.physical(hilb))
+    ρ = zeros(out_type(c.net), D, D)
+    check(c.ctx, ccall((:nq_fullspace_state, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), c.h, norm ? 1 : 0, ρ))
+    return ρ
+end
+# init_sampler!(::ExactSampler): the cumulative table; samplenext!: basis numbers for L slots x B chains
+function exact_table!(pdf::Vector{Float64}, c::CudaNet)
+    check(c.ctx, ccall((:nq_exact_table, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), c.h, pdf))
+    return pdf
+end
+function exact_sample!(indices::Matrix{Int64}, prow::Matrix{UInt64}, pcol, c::CudaNet, pdf::Vector{Float64}; seed, chain_offset = 0,
+                       draw_base = 0, uniforms = nothing)
+    B, L = size(indices)
+    check(c.ctx, ccall((:nq_exact_sample, lib), Cint,
+                       (Ptr{Cvoid}, Ptr{Float64}, UInt64, Int64, UInt64, Int64, Int64, Ptr{Float64}, Ptr{UInt64}, Ptr{UInt64}, Ptr{Int64}),
+                       c.h, pdf, seed, chain_offset, draw_base, B, L, uniforms === nothing ? C_NULL : uniforms, prow,
+                       pcol === nothing ? C_NULL : pcol, indices))
+    return indices
+end
+
+# ---- NDMSymm (Networks/MixedDensityMatrix/NDMSymm.jl, NDMSymmBatched.jl) ---------------------------------------------
+# The gather lists are the rows of the reference's own 0/1 matrices (net.∇b_mat ... net.∇u_mat) and set_bare_params!'s
+# index map; they are built once from those matrices.
+mutable struct CudaSymm
+    ctx::Ctx
+    h::Ptr{Cvoid}
+    bare::CudaNet
+    Ps::Int
+end
+function CudaSymm(bare::CudaNet, ptr::Vector{Int64}, idx::Vector{Int32}, scale::Vector{Float64}, src::Vector{Int32},
+                  avg_ranges::Matrix{Int64})
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    Ps = length(scale)
+    check(bare.ctx, ccall((:nq_symm_create, lib), Cint,
+                          (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Cint, Ptr{Int64}, Ptr{Ptr{Cvoid}}),
+                          bare.h, Ps, ptr, idx, scale, src, size(avg_ranges, 2), avg_ranges, h))
+    g = CudaSymm(bare.ctx, h[], bare, Ps)
+    finalizer(g -> (g.h != C_NULL && ccall((:nq_symm_destroy, lib), Cint, (Ptr{Cvoid},), g.h); g.h = C_NULL), g)
+    return g
+end
+set_params!(g::CudaSymm, w::Vector) = check(g.ctx, ccall((:nq_symm_set_params, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), g.h, w, length(w)))
+get_params!(w::Vector, g::CudaSymm) = (check(g.ctx, ccall((:nq_symm_get_params, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), g.h, w, length(w))); w)
+update!(g::CudaSymm, Δw::AbstractVector, η::Real) =                     # NDMSymm.jl:27-30: step, then set_bare_params!
+    check(g.ctx, ccall((:nq_symm_update, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble), g.h, Δw, η))
+function symmetrize_∇logψ!(∇symm::AbstractMatrix, g::CudaSymm, ∇bare::AbstractMatrix)    # NDMSymmBatched.jl:22-36
+    check(g.ctx, ccall((:nq_symm_gradient, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Cint, Ptr{Cvoid}, Int64),
+                       g.h, ∇bare, size(∇bare, 1), size(∇bare, 2), nqdtype(∇bare), ∇symm, size(∇symm, 1)))
+    return ∇symm
+end
+
+# ---- streaming S assembly (O never materialised for the whole batch) and the Nesterov step ---------------------------
+function sr_accumulate!(ctx::Ctx, Sacc, sumO, Ochunk::AbstractMatrix, Ns_total::Integer, real_params::Bool, first::Bool)
+    P, Nc = size(Ochunk)
+    check(ctx, ccall((:nq_sr_accumulate, lib), Cint,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                     ctx.h, Ochunk, P, P, Nc, Ns_total, nqdtype(Ochunk), real_params ? 1 : 0, Sacc, sumO, first ? 1 : 0))
+end
+sr_finish!(ctx::Ctx, Sacc, sumO, P::Integer, Ns_total::Integer, T::Type, real_params::Bool) =
+    check(ctx, ccall((:nq_sr_finish, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Cint, Cint),
+                     ctx.h, Sacc, sumO, P, Ns_total, nqdtype(T), real_params ? 1 : 0))
+# Optimisers.apply(o::Nesterov, x, Δ, state) on device vectors (rules.jl:44-55): returns -d in `delta`
+nesterov!(ctx::Ctx, delta, velocity, Δ, n::Integer, T::Type, o) =
+    check(ctx, ccall((:nq_nesterov, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Cdouble, Cdouble, Ptr{Cvoid}),
+                     ctx.h, velocity, Δ, n, nqdtype(T), o.lr, o.μ, delta))
+
 end # module

@@ -61,6 +61,8 @@ struct nq_operator_s {
 int nq_pack_device(nq_ctx_t ctx, nq_hilbert h, int N, int64_t B, const void* dsigma, nq_dtype sdtype, uint64_t* dpacked);
 int nq_unpack_device(nq_ctx_t ctx, nq_hilbert h, int N, int64_t B, const uint64_t* dpacked, void* dsigma, nq_dtype sdtype);
 int nq_machine_ensure_tables(nq_machine_t m);
+// RBM / RBMSplit: tables of the register-resident sampler, [sign][mat][k + M j] = exp(+-c g W) - 1, then wsum[mat][j]
+const void* nq_machine_qtab(nq_machine_t m);
 int nq_machine_eval_device(nq_machine_t m, const uint64_t* prow, const uint64_t* pcol, int64_t B,
                            void* out, void* O, int64_t ldO);
 struct NqStage;

@@ -322,6 +322,34 @@ __global__ void etab_kernel(const E* __restrict__ w, E* __restrict__ out, int64_
     out[i] = e_exp(x);
     out[n + i] = e_exp(-x);
 }
+// Tables of the register-resident RBM sampler (nq_sampler.cu, sampler_rbm_reg_kernel).  log cosh(theta) = softplus(2 theta)
+// - theta - ln 2, so both activations run the softplus recurrence on q = sigmoid(g theta) (g = 2 for logcosh, 1 for
+// softplus):  out[sign][i] = exp(+-c g w_i) - 1 (expm1-accurate), followed by wsum[mat][j] = sum_k W_kj (the -theta term).
+__device__ __forceinline__ float em1(float x) { return expm1f(x); }
+__device__ __forceinline__ double em1(double x) { return expm1(x); }
+template <typename T> __device__ __forceinline__ cx<T> em1(cx<T> z) {
+    T sy, cy, sh, ch;
+    m_sincos(z.im, &sy, &cy);
+    m_sincos(T(0.5) * z.im, &sh, &ch);
+    const T e = em1(z.re);
+    return cx<T>(e * cy - T(2) * sh * sh, (e + T(1)) * sy);     // e^x cos y - 1 = expm1(x) cos y - 2 sin^2(y/2)
+}
+template <typename E>
+__global__ void qtab_kernel(const E* __restrict__ w, E* __restrict__ out, int64_t n, typename elem_traits<E>::real c) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    E x = rscale(c, w[i]);
+    out[i] = em1(x);
+    out[n + i] = em1(-x);
+}
+template <typename E>
+__global__ void wsum_kernel(const E* __restrict__ w, E* __restrict__ out, int M, int ncol) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncol) return;
+    E s = make_zero<E>();
+    for (int k = 0; k < M; k++) s += w[k + (int64_t)M * j];
+    out[j] = s;
+}
 // NDM ancilla tables: out[sign][a + A j] = exp(+-(c/2) (u_lam + i u_mu))
 template <typename T>
 __global__ void etab_pi_kernel(const T* __restrict__ ul, const T* __restrict__ um, cx<T>* __restrict__ out, int64_t n, T c) {
@@ -443,7 +471,13 @@ static size_t etab_bytes(nq_machine_t m) {
     const int64_t MN = (int64_t)m->M * m->N, AN = (int64_t)m->A * m->N;
     const size_t es = nq_dtype_size(m->dtype);
     if (m->kind == NQ_NDM) return ((size_t)4 * MN * es + 15) / 16 * 16 + (size_t)2 * AN * 2 * es;
-    return (size_t)2 * (m->kind == NQ_RBMSPLIT ? 2 : 1) * MN * es;
+    // RBM / RBMSplit: [exp tables 2 nmat MN][q tables 2 nmat MN][wsum nmat N]  (nq_machine_qtab)
+    const size_t nmat = m->kind == NQ_RBMSPLIT ? 2 : 1;
+    return ((size_t)4 * nmat * MN + nmat * m->N) * es;
+}
+const void* nq_machine_qtab(nq_machine_t m) {
+    const size_t nmat = m->kind == NQ_RBMSPLIT ? 2 : 1;
+    return (const char*)m->etab + (size_t)2 * nmat * m->M * m->N * nq_dtype_size(m->dtype);
 }
 
 template <typename E>
@@ -456,6 +490,9 @@ static int build_tables_rbm(nq_machine_t m) {
     const E* W = (const E*)m->params + (m->kind == NQ_RBMSPLIT ? 2 * m->N : m->N) + m->M;
     T c = m->hilb == NQ_SPIN ? T(2) : T(1);
     NQ_LAUNCH(ctx, etab_kernel<E>, (unsigned)((n + 255) / 256), 256, 0, W, (E*)m->etab, n, c);
+    const T g = m->act == NQ_LOGCOSH ? T(2) : T(1);
+    NQ_LAUNCH(ctx, qtab_kernel<E>, (unsigned)((n + 255) / 256), 256, 0, W, (E*)m->etab + 2 * n, n, c * g);
+    NQ_LAUNCH(ctx, wsum_kernel<E>, (unsigned)((nmat * m->N + 127) / 128), 128, 0, W, (E*)m->etab + 4 * n, m->M, nmat * m->N);
     return NQ_OK;
 }
 

@@ -37,6 +37,11 @@ struct nq_sampler_s {
 namespace {
 
 constexpr int MAXW = 4;   // N <= 256
+// The tracked f' values follow accepted moves exactly (in exact arithmetic); they are rebuilt from the configuration at the
+// start of every launch and then every REFRESH_STEPS stored steps, which bounds the accumulated rounding (~1e-16 per
+// accepted move) without paying a full pass over the weights per step: on cfg3 that pass moved as many bytes as all the
+// proposals of the step.
+constexpr int REFRESH_STEPS = 16;
 
 struct Philox {
     uint32_t k0, k1;
@@ -129,35 +134,56 @@ struct DrawBatch {
 };
 
 // ---- RBM / RBMSplit -------------------------------------------------------------------
-// Per chain (warp) only s_k = f'(theta_k) is tracked: with the per-parameter tables Ep = exp(+-c W_kj) a
-// proposal costs one table load, a few multiply-adds and one division per hidden unit -- no transcendental --
-//   psi(eta)/psi(sigma) = e^{a_j dv} prod_k [1 + s_k (Ep - 1)]      (softplus; see ratio_step for logcosh)
-// and an accepted move updates s_k in place.  s is recomputed from the configuration once per stored sample.
-template <typename E, int ACT, bool DOUBLED>
-__global__ void sampler_rbm_kernel(const E* __restrict__ par, const E* __restrict__ tab, uint64_t* __restrict__ st_row,
-                                   uint64_t* __restrict__ st_col, RunArgs a) {
+// log cosh(theta) = softplus(2 theta) - theta - ln 2, so both activations run ONE recurrence on q_k = sigmoid(g theta_k)
+// (g = 2 logcosh, 1 softplus; q = (1 + tanh theta)/2 or f'(theta), no extra transcendental):
+//   psi(eta)/psi(sigma) = e^{dv (a_j - [logcosh] sum_k W_kj)} prod_k [1 + q_k T_kj],   T = exp(+-c g W_kj) - 1
+//   accepted move:  q_k <- q_k (1 + T_kj) / (1 + q_k T_kj)
+// A proposal is one 16-byte table load and one complex multiply-add per hidden unit.  The first version kept the tanh
+// values in shared memory and read two table entries per unit (exp(+-c W)); it was bound by L1 / shared-memory bandwidth
+// (cfg3: 61 M proposals x 144 units x 64 B = 21 TB/s).  Here q, T and the factors of the current proposal live in
+// REGISTERS (KU = ceil(M / 32) units per lane), so a proposal moves 16 B per unit and an accepted one nothing more.
+// theta is rebuilt from the configuration once per stored sample from site values staged per warp.
+__device__ __forceinline__ double fast_rcp(double x) {           // MUFU.RCP64H seed + cubic step, ~1 ulp, no slow path
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float q_div(float a, float b) { return a * fast_rcp(b); }
+__device__ __forceinline__ double q_div(double a, double b) { return a * fast_rcp(b); }
+template <typename T> __device__ __forceinline__ cx<T> q_div(cx<T> a, cx<T> b) {
+    const T inv = fast_rcp(b.re * b.re + b.im * b.im);
+    return cx<T>((a.re * b.re + a.im * b.im) * inv, (a.im * b.re - a.re * b.im) * inv);
+}
+
+template <typename E, int ACT, bool DOUBLED, int KU>
+__global__ void __launch_bounds__(256) sampler_rbm_reg_kernel(const E* __restrict__ par, const E* __restrict__ qtab,
+                                                               uint64_t* __restrict__ st_row, uint64_t* __restrict__ st_col, RunArgs a) {
     typedef typename elem_traits<E>::real T;
-    typedef decltype(to_d(E())) PD;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int64_t chain = blockIdx.x * (int64_t)wpb + warp;
     const int N = a.N, M = a.M, W64 = (N + 63) >> 6;
     const int64_t off_b = DOUBLED ? 2 * N : N;
-    // eb[(sign * nmat + mat) * N + j] = |exp(dv a_j)|^2 for the two possible flips of site j (CTA-wide table)
+    const int64_t MN = (int64_t)M * N;
+    constexpr int nmat = DOUBLED ? 2 : 1;
+    const E* __restrict__ wsum = qtab + 2 * nmat * MN;
+    // eb[(sign * nmat + mat) * N + j] = |exp(dv (a_j - [logcosh] sum_k W_kj))|^2 for the two flips of site j (CTA-wide)
     T* eb = (T*)smem_raw;
-    for (int i = threadIdx.x; i < 2 * (DOUBLED ? 2 : 1) * N; i += blockDim.x) {
-        const int nm = DOUBLED ? 2 : 1, sgn = i / (nm * N), rem = i - sgn * nm * N, mt = rem / N, jj = rem - mt * N;
+    for (int i = threadIdx.x; i < 2 * nmat * N; i += blockDim.x) {
+        const int sgn = i / (nmat * N), rem = i - sgn * nmat * N, mt = rem / N, jj = rem - mt * N;
         const T dvv = a.hilb == NQ_SPIN ? (sgn ? T(-2) : T(2)) : (sgn ? T(-1) : T(1));
-        eb[i] = (T)abs2_d(e_exp(rscale(dvv, par[(mt ? N : 0) + jj])));
+        E lin = par[(mt ? N : 0) + jj];
+        if (ACT == NQ_LOGCOSH) lin = lin - wsum[mt * N + jj];
+        eb[i] = (T)abs2_d(e_exp(rscale(dvv, lin)));
     }
     __syncthreads();
     if (chain >= a.B) return;
-    E* sk = (E*)(smem_raw + ((size_t)4 * N * sizeof(T) + 15) / 16 * 16) + (size_t)warp * 3 * M;
-    E* ts = sk + M;               // [2M]: numerators, then factors
+    const int nsv = DOUBLED ? 2 * N : N;
+    T* vsw = (T*)(smem_raw + ((size_t)4 * N * sizeof(T) + 15) / 16 * 16) + (size_t)warp * ((nsv + 1) & ~1);
     const E* __restrict__ Wr = par + off_b + M;
-    const E* __restrict__ Wc = Wr + (int64_t)M * N;
-    const int64_t MN = (int64_t)M * N;
-    const int nmat = DOUBLED ? 2 : 1;
     uint64_t rb[MAXW], cb[MAXW];
 #pragma unroll
     for (int w = 0; w < MAXW; w++) {
@@ -167,56 +193,66 @@ __global__ void sampler_rbm_kernel(const E* __restrict__ par, const E* __restric
     const int nsites = DOUBLED ? 2 * N : N;
     unsigned nacc = 0;
     const int nsteps = a.burn + a.L;
+    E q[KU];
     for (int step = 0; step < nsteps; step++) {
-        for (int k = lane; k < M; k += 32) {
-            E t = par[off_b + k];
-            for (int j = 0; j < N; j++) {
-                t += rscale(digit_value<T>(a.hilb, get_bit(rb, j)), Wr[k + (int64_t)M * j]);
-                if (DOUBLED) t += rscale(digit_value<T>(a.hilb, get_bit(cb, j)), Wc[k + (int64_t)M * j]);
+        if (step % REFRESH_STEPS == 0) {
+        for (int i = lane; i < nsv; i += 32) vsw[i] = digit_value<T>(a.hilb, get_bit(i < N ? rb : cb, i < N ? i : i - N));
+        __syncwarp();
+        {   // Wr and Wc are contiguous: column i of the [M, nsv] matrix belongs to vsw[i]
+            E t[KU];
+#pragma unroll
+            for (int u = 0; u < KU; u++) t[u] = lane + 32 * u < M ? par[off_b + lane + 32 * u] : make_zero<E>();
+            for (int i = 0; i < nsv; i++) {
+                const T v = vsw[i];
+                const E* __restrict__ wc = Wr + (int64_t)M * i + lane;
+#pragma unroll
+                for (int u = 0; u < KU; u++) if (lane + 32 * u < M) t[u] += rscale(v, wc[32 * u]);
             }
-            E f, d;
-            act_eval<ACT>(t, f, d);
-            sk[k] = d;
+#pragma unroll
+            for (int u = 0; u < KU; u++) {
+                E f, d;
+                act_eval<ACT>(t[u], f, d);
+                q[u] = ACT == NQ_LOGCOSH ? rscale(T(0.5), e_one<E>() + d) : d;
+            }
         }
         __syncwarp();
+        }
         DrawBatch<T> db;
 #pragma unroll 1
         for (int ps = 0; ps < a.passes; ps++) {
             int pic = step * a.passes + ps;
             if ((ps & 31) == 0) db.fill(a, chain, pic, a.passes - ps, nsites, lane);
-            int site; T u;
-            db.get(ps & 31, site, u);
+            int site; T u01;
+            db.get(ps & 31, site, u01);
             const bool col = DOUBLED && site >= N;
             const int j = col ? site - N : site;
             const T dv = flip_delta<T>(a.hilb, get_bit(col ? cb : rb, j));
             const int sg = dv > T(0) ? 0 : 1, mat = col ? 1 : 0;
-            const E* __restrict__ tp = tab + (int64_t)(sg * nmat + mat) * MN + (int64_t)M * j;
-            const E* __restrict__ tm = tab + (int64_t)((1 - sg) * nmat + mat) * MN + (int64_t)M * j;
-            // |psi(eta)/psi(sigma)|^2 = |e^{a_j dv}|^2 prod_k |fac_k|^2: one real product; the new s_k = num / den
-            // is only formed when the move is accepted
+            const E* __restrict__ tp = qtab + (int64_t)(sg * nmat + mat) * MN + (int64_t)M * j + lane;
+            E Tk[KU], fac[KU];
             double prod = 1.0;
-            for (int k = lane; k < M; k += 32) {
-                E Ep = tp[k], Em = ACT == NQ_LOGCOSH ? tm[k] : e_one<E>();
-                E fac, num;
-                ratio_parts<ACT>(sk[k], Ep, Em, fac, num);
-                prod *= abs2_d(fac);
-                ts[k] = num; ts[M + k] = fac;
+#pragma unroll
+            for (int u = 0; u < KU; u++) {
+                Tk[u] = lane + 32 * u < M ? tp[32 * u] : make_zero<E>();
+                fac[u] = e_one<E>() + e_mul(q[u], Tk[u]);
+                prod *= abs2_d(fac[u]);
             }
             prod = warp_prod(prod);
             const double pr = prod * (double)eb[(sg * nmat + mat) * N + j];
-            const bool acc = (u - (T)pr) < T(0);
+            const bool acc = (u01 - (T)pr) < T(0);
             if (acc) {
-                for (int k = lane; k < M; k += 32) sk[k] = ratio_finish<ACT>(ts[M + k], ts[k]);
+#pragma unroll
+                for (int u = 0; u < KU; u++) q[u] = q_div(q[u] + e_mul(q[u], Tk[u]), fac[u]);
                 if (col) cb[j >> 6] ^= 1ull << (j & 63); else rb[j >> 6] ^= 1ull << (j & 63);
                 nacc++;
             }
-            __syncwarp();
             if (a.replay && a.accept_out && lane == 0) a.accept_out[(int64_t)pic * a.B + chain] = acc ? 1 : 0;
         }
         if (step >= a.burn && a.out_prow && lane == 0) {
             int64_t o = ((int64_t)(step - a.burn) * a.B + chain) * W64;
             for (int w = 0; w < W64; w++) { a.out_prow[o + w] = rb[w]; if (DOUBLED && a.out_pcol) a.out_pcol[o + w] = cb[w]; }
         }
+        __syncwarp();
     }
     if (lane == 0) {
         for (int w = 0; w < W64; w++) { st_row[chain * W64 + w] = rb[w]; if (DOUBLED) st_col[chain * W64 + w] = cb[w]; }
@@ -265,6 +301,7 @@ __global__ void sampler_ndm_kernel(const T* __restrict__ par, const T* __restric
     unsigned nacc = 0;
     const int nsteps = a.burn + a.L;
     for (int step = 0; step < nsteps; step++) {
+        if (step % REFRESH_STEPS == 0) {
         for (int i = lane; i < 2 * N; i += 32) vsw[i] = digit_value<T>(a.hilb, get_bit(i < N ? rb : cb, i < N ? i : i - N));
         __syncwarp();
         for (int k = lane; k < M; k += 32) {
@@ -292,6 +329,7 @@ __global__ void sampler_ndm_kernel(const T* __restrict__ par, const T* __restric
             spi[q] = d;
         }
         __syncwarp();
+        }
         DrawBatch<T> db;
 #pragma unroll 1
         for (int ps = 0; ps < a.passes; ps++) {
@@ -649,21 +687,34 @@ int run_sampler_rule(nq_sampler_t s, const RunArgs& a) {
     }
 }
 
-template <typename E, int ACT, bool DOUBLED>
-int launch_sampler_rbm(nq_sampler_t s, const RunArgs& a) {
+template <typename E, int ACT, bool DOUBLED, int KU>
+int launch_sampler_rbm_ku(nq_sampler_t s, const RunArgs& a) {
+    typedef typename elem_traits<E>::real T;
     nq_machine_t m = s->m;
     nq_ctx_t ctx = m->ctx;
-    size_t per_warp = (size_t)3 * m->M * sizeof(E);
-    const size_t tab_bytes = ((size_t)4 * m->N * sizeof(typename elem_traits<E>::real) + 15) / 16 * 16;
-    int wpb = 8;
-    while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
-    size_t smem = tab_bytes + per_warp * wpb;
-    if (smem > ctx->smem_optin) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "sampler needs %zu B shared memory per chain", per_warp);
-    auto kern = sampler_rbm_kernel<E, ACT, DOUBLED>;
+    const int nsv = (DOUBLED ? 2 : 1) * m->N;
+    const int wpb = 8;
+    const size_t smem = ((size_t)4 * m->N * sizeof(T) + 15) / 16 * 16 + (size_t)wpb * ((nsv + 1) & ~1) * sizeof(T);
+    if (smem > ctx->smem_optin) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "sampler needs %zu B shared memory", smem);
+    auto kern = sampler_rbm_reg_kernel<E, ACT, DOUBLED, KU>;
     NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((s->B + wpb - 1) / wpb);
-    NQ_LAUNCH(ctx, kern, grid, wpb * 32, smem, (const E*)m->params, (const E*)m->etab, s->prow, s->pcol, a);
+    NQ_LAUNCH(ctx, kern, grid, wpb * 32, smem, (const E*)m->params, (const E*)nq_machine_qtab(m), s->prow, s->pcol, a);
     return NQ_OK;
+}
+
+template <typename E, int ACT, bool DOUBLED>
+int launch_sampler_rbm(nq_sampler_t s, const RunArgs& a) {
+    const int M = s->m->M;
+    if (M <= 32) return launch_sampler_rbm_ku<E, ACT, DOUBLED, 1>(s, a);
+    if (M <= 64) return launch_sampler_rbm_ku<E, ACT, DOUBLED, 2>(s, a);
+    if (M <= 96) return launch_sampler_rbm_ku<E, ACT, DOUBLED, 3>(s, a);
+    if (M <= 128) return launch_sampler_rbm_ku<E, ACT, DOUBLED, 4>(s, a);
+    if (M <= 160) return launch_sampler_rbm_ku<E, ACT, DOUBLED, 5>(s, a);
+    if (M <= 256) return launch_sampler_rbm_ku<E, ACT, DOUBLED, 8>(s, a);
+    if (M <= 512) return launch_sampler_rbm_ku<E, ACT, DOUBLED, 16>(s, a);
+    if (M <= 1024) return launch_sampler_rbm_ku<E, ACT, DOUBLED, 32>(s, a);
+    return nq_fail(s->m->ctx, NQ_ERR_UNSUPPORTED, "sampler supports M <= 1024 hidden units (M = %d)", M);
 }
 
 template <typename T, int ACT>

@@ -614,18 +614,19 @@ template <typename TS_>
 __global__ void syrk_finalize_kernel(const double* __restrict__ Wre, const double* __restrict__ Wim, int nsplit,
                                      int64_t Ppad, int64_t P, double scale, int out_complex, TS_* __restrict__ S) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    int64_t l = blockIdx.y;
-    if (k >= P || l >= P) return;
-    bool lower = (k / TS) >= (l / TS);
-    int64_t r = lower ? k : l, c = lower ? l : k;
-    double re = 0.0, im = 0.0;
-    for (int s = 0; s < nsplit; s++) {
-        re += Wre[(size_t)s * Ppad * Ppad + r + Ppad * c];
-        if (Wim) im += Wim[(size_t)s * Ppad * Ppad + r + Ppad * c];
+    if (k >= P) return;
+    for (int64_t l = blockIdx.y; l < P; l += gridDim.y) {        // grid.y is capped at 65535
+        bool lower = (k / TS) >= (l / TS);
+        int64_t r = lower ? k : l, c = lower ? l : k;
+        double re = 0.0, im = 0.0;
+        for (int s = 0; s < nsplit; s++) {
+            re += Wre[(size_t)s * Ppad * Ppad + r + Ppad * c];
+            if (Wim) im += Wim[(size_t)s * Ppad * Ppad + r + Ppad * c];
+        }
+        if (!lower) im = -im;
+        if (out_complex) { S[2 * (k + P * l)] = (TS_)(re * scale); S[2 * (k + P * l) + 1] = (TS_)(im * scale); }
+        else S[k + P * l] = (TS_)(re * scale);
     }
-    if (!lower) im = -im;
-    if (out_complex) { S[2 * (k + P * l)] = (TS_)(re * scale); S[2 * (k + P * l) + 1] = (TS_)(im * scale); }
-    else S[k + P * l] = (TS_)(re * scale);
 }
 
 template <typename T, int NC>
@@ -1178,6 +1179,15 @@ __global__ void __launch_bounds__(256) chol_fused_kernel(E* __restrict__ A, int6
                 while ((int64_t)bi * (bi + 1) / 2 > t) bi--;
                 const int bj = (int)(t - (int64_t)bi * (bi + 1) / 2);
                 const int64_t i0 = base + (int64_t)bi * 32, l0 = base + (int64_t)bj * 32;
+                // the C tile is read-modified-written once, after the k loop, and usually comes from HBM (the trailing matrix
+                // does not fit in L2): start those lines moving now so that the epilogue finds them in L2
+                {
+                    constexpr int LPC = CPLX ? 4 : 2;                // 128-byte lines per 32-row column segment
+                    for (int q = lane; q < 32 * LPC; q += 32) {
+                        const int64_t col = l0 + q / LPC, row = i0 + (q % LPC) * (32 / LPC);
+                        if (row < P && col < P) asm volatile("prefetch.global.L2 [%0];" ::"l"(Ad + (row + P * col) * NPL));
+                    }
+                }
                 double cre[4][4][2], cim[CPLX ? 4 : 1][CPLX ? 4 : 1][2];
 #pragma unroll
                 for (int i = 0; i < 4; i++)
@@ -2020,7 +2030,7 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
         if (nq_dtype_is_double(dtype)) NQ_CHECK((launch_syrk<double, 1>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
         else NQ_CHECK((launch_syrk<float, 1>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
     }
-    dim3 grid((unsigned)((P + 127) / 128), (unsigned)P);
+    dim3 grid((unsigned)((P + 127) / 128), (unsigned)std::min<int64_t>(P, 65535));
     const double scale = 1.0 / (double)Ns_total;
     if (nq_dtype_is_double(dtype))
         NQ_LAUNCH(ctx, syrk_finalize_kernel<double>, grid, 128, 0, (const double*)Wre, (const double*)Wim, nsplit, Ppad, P, scale, (int)out_complex, (double*)dS);
@@ -2244,6 +2254,149 @@ extern "C" int nq_sr_solve_matfree_algo(nq_ctx_t ctx, const void* Oc, int64_t ld
                                         nq_dtype dtype, const void* F, int real_params, double eps, nq_solver algo, double tol,
                                         int64_t maxiter, void* dw, int64_t* iters) {
     return sr_solve_matfree_impl(ctx, Oc, ldO, P, Ns, Ns_total, dtype, F, real_params, eps, algo, tol, maxiter, dw, iters);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming S assembly: batches whose gradient matrix does not fit in memory (BASELINE cfg5: O > 60 GB) are produced
+// chunk by chunk (nq_logpsi_grad_packed into ONE reused [P, Nc] buffer) and consumed at once.  The rows are shifted by
+// a PROVISIONAL mean c (the mean of the first chunk) before they enter the Gram matrix, so the final centring
+//     S = sum_chunks (O_c - c)(O_c - c)^H / Ns  -  (a - c)(a - c)^H,        a = <O> = c + sum (O - c) / Ns
+// subtracts a term of the order of the statistical error of c instead of |<O>|^2: no cancellation in either precision.
+// ref: the same S as SRDirect.jl:26-49 on the centred rows of BaseIterativeSampler.jl:19-26.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+template <typename T> __global__ void acc_add_kernel(T* __restrict__ acc, const T* __restrict__ x, int64_t n, int first) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (; i < n; i += (int64_t)gridDim.x * blockDim.x) acc[i] = first ? x[i] : acc[i] + x[i];
+}
+// state = [running sum of (O - c) | shift c]; cs = column sums of the UNshifted chunk
+// first chunk: c = csg / count with csg the column sums of the first chunks of ALL ranks (= cs on one GPU)
+__global__ void stream_shift_kernel(cxd* __restrict__ state, const cxd* __restrict__ cs, const cxd* __restrict__ csg,
+                                    int64_t P, int64_t Nc, int first) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    if (first) {
+        const double cnt = csg[P].re;
+        state[P + i] = cxd(csg[i].re / cnt, csg[i].im / cnt);
+        state[i] = cxd(0.0, 0.0);
+    }
+    const cxd c = state[P + i];
+    state[i] = cxd(state[i].re + (cs[i].re - (double)Nc * c.re), state[i].im + (cs[i].im - (double)Nc * c.im));
+}
+// S(i,j) -= Re(d_i conj(d_j)) (real S) or conj(d_i) d_j (complex S), d = sum (O - c) / Ns_total; avg = c + d
+template <typename T> __global__ void rank1_center_kernel(T* __restrict__ S, int64_t P, const cxd* __restrict__ state, double inv, int out_complex) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const double ar = state[i].re * inv, ai = state[i].im * inv;
+    for (int64_t j = blockIdx.y; j < P; j += gridDim.y) {
+        const double br = state[j].re * inv, bi = state[j].im * inv;
+        if (out_complex) {
+            S[2 * (i + P * j)] = (T)((double)S[2 * (i + P * j)] - (ar * br + ai * bi));
+            S[2 * (i + P * j) + 1] = (T)((double)S[2 * (i + P * j) + 1] - (ar * bi - ai * br));
+        } else {
+            S[i + P * j] = (T)((double)S[i + P * j] - (ar * br + ai * bi));
+        }
+    }
+}
+__global__ void stream_avg_kernel(cxd* __restrict__ state, int64_t P, double inv) {       // state[0..P) <- <O>
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < P) state[i] = cxd(state[P + i].re + state[i].re * inv, state[P + i].im + state[i].im * inv);
+}
+}  // namespace
+
+extern "C" int nq_sr_accumulate(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, int64_t Nc, int64_t Ns_total, nq_dtype dtype,
+                                int real_params, void* Sacc, void* state, int first) {
+    if (!ctx || !O || !Sacc || !state || P <= 0 || Nc <= 0 || ldO < P || Ns_total < Nc) return NQ_ERR_ARG;
+    if (!nq_is_device_ptr(O) || !nq_is_device_ptr(Sacc) || !nq_is_device_ptr(state))
+        return nq_fail(ctx, NQ_ERR_ARG, "nq_sr_accumulate works on device-resident buffers");
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool ocx = nq_dtype_is_complex(dtype), out_complex = ocx && !real_params;
+    const nq_dtype sdt = out_complex ? dtype : nq_real_of(dtype);
+    const size_t sbytes = (size_t)P * P * nq_dtype_size(sdt);
+    cxd* cs = (cxd*)nq_scratch(ctx, SL_W2, (size_t)(2 * P + 2) * sizeof(cxd));
+    if (!cs) return NQ_ERR_ALLOC;
+    cxd* csg = cs + P + 1;                 // [P] column sums + [1] sample count of the first chunks of all ranks
+    NQ_CHECK(colsum_dispatch<false>(ctx, dtype, O, ldO, P, Nc, nullptr, 1.0, cs));
+    if (first) {
+        const cxd cnt((double)Nc, 0.0);
+        NQ_CUDA(ctx, cudaMemcpyAsync(csg, cs, (size_t)P * sizeof(cxd), cudaMemcpyDeviceToDevice, ctx->stream));
+        NQ_CUDA(ctx, cudaMemcpyAsync(csg + P, &cnt, sizeof(cxd), cudaMemcpyHostToDevice, ctx->stream));
+        NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // cnt lives on the host stack
+        // shards: the SAME shift on every rank, so that the partial sums of nq_sr_finish are plain sums
+        if (ctx->nccl_comm) NQ_CHECK(nq_allreduce_device(ctx, csg, P + 1, NQ_C128, false));
+    }
+    NQ_LAUNCH(ctx, stream_shift_kernel, (unsigned)((P + 255) / 256), 256, 0, (cxd*)state, (const cxd*)cs, (const cxd*)csg, P, Nc, first);
+    {   // O_c <- O_c - c in place (the chunk buffer is the caller's scratch)
+        dim3 grid((unsigned)((P + 127) / 128), (unsigned)std::min<int64_t>(Nc, 4096));
+        const cxd* c = (const cxd*)state + P;
+        switch (dtype) {
+            case NQ_F32: NQ_LAUNCH(ctx, subtract_avg_kernel<float>, grid, 128, 0, (float*)O, ldO, P, Nc, c); break;
+            case NQ_F64: NQ_LAUNCH(ctx, subtract_avg_kernel<double>, grid, 128, 0, (double*)O, ldO, P, Nc, c); break;
+            case NQ_C64: NQ_LAUNCH(ctx, subtract_avg_kernel<cxf>, grid, 128, 0, (cxf*)O, ldO, P, Nc, c); break;
+            default: NQ_LAUNCH(ctx, subtract_avg_kernel<cxd>, grid, 128, 0, (cxd*)O, ldO, P, Nc, c); break;
+        }
+    }
+    // chunk Gram matrix with the global normalisation into a scratch S (the first chunk goes straight to Sacc)
+    void* St = first ? Sacc : nq_scratch(ctx, SL_HOSTG, sbytes);
+    void* zg = nq_scratch(ctx, SL_IN4, (size_t)2 * P * sizeof(cxd));
+    if (!St || !zg) return NQ_ERR_ALLOC;
+    NQ_CUDA(ctx, cudaMemsetAsync(zg, 0, (size_t)P * sizeof(cxd), ctx->stream));
+    NQ_CHECK(nq_sr_setup(ctx, O, ldO, P, Nc, Ns_total, dtype, zg, real_params, St, (char*)zg + (size_t)P * sizeof(cxd)));
+    if (!first) {
+        const int64_t n = (int64_t)(sbytes / (nq_dtype_is_double(dtype) ? 8 : 4));
+        const unsigned g = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->num_sms * 16);
+        if (nq_dtype_is_double(dtype)) NQ_LAUNCH(ctx, acc_add_kernel<double>, g, 256, 0, (double*)Sacc, (const double*)St, n, 0);
+        else NQ_LAUNCH(ctx, acc_add_kernel<float>, g, 256, 0, (float*)Sacc, (const float*)St, n, 0);
+    }
+    return NQ_OK;
+}
+
+extern "C" int nq_sr_finish(nq_ctx_t ctx, void* Sacc, void* state, int64_t P, int64_t Ns_total, nq_dtype dtype, int real_params) {
+    if (!ctx || !Sacc || !state || P <= 0 || Ns_total <= 0) return NQ_ERR_ARG;
+    if (!nq_is_device_ptr(Sacc) || !nq_is_device_ptr(state)) return nq_fail(ctx, NQ_ERR_ARG, "nq_sr_finish works on device-resident buffers");
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool out_complex = nq_dtype_is_complex(dtype) && !real_params;
+    if (ctx->nccl_comm) {
+        // shards: every rank used the same shift (all-reduced in the first nq_sr_accumulate), so partial S and partial
+        // sums of (O - c) are plain sums
+        const nq_dtype sdt = out_complex ? dtype : nq_real_of(dtype);
+        NQ_CHECK(nq_allreduce_device(ctx, Sacc, P * P, sdt, false));
+        NQ_CHECK(nq_allreduce_device(ctx, state, P, NQ_C128, false));
+    }
+    dim3 grid((unsigned)((P + 127) / 128), (unsigned)std::min<int64_t>(P, 65535));
+    const double inv = 1.0 / (double)Ns_total;
+    if (nq_dtype_is_double(dtype)) NQ_LAUNCH(ctx, rank1_center_kernel<double>, grid, 128, 0, (double*)Sacc, P, (const cxd*)state, inv, (int)out_complex);
+    else NQ_LAUNCH(ctx, rank1_center_kernel<float>, grid, 128, 0, (float*)Sacc, P, (const cxd*)state, inv, (int)out_complex);
+    NQ_LAUNCH(ctx, stream_avg_kernel, (unsigned)((P + 255) / 256), 256, 0, (cxd*)state, P, inv);
+    return NQ_OK;
+}
+
+// Nesterov(lr, mu) (Optimisers/rules.jl:36-55) on device vectors of the machine dtype: with the velocity v of the
+// parameter vector,  d = mu^2 v - (1 + mu) lr dw;  v <- mu v - lr dw;  delta = -d  (the caller applies w <- w - delta).
+namespace {
+template <typename E> __global__ void nesterov_kernel(E* __restrict__ v, const E* __restrict__ dw, E* __restrict__ delta,
+                                                      typename elem_traits<E>::real lr, typename elem_traits<E>::real mu, int64_t n) {
+    typedef typename elem_traits<E>::real T;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const E vi = v[i], gi = dw[i];
+    delta[i] = rscale((T(1) + mu) * lr, gi) - rscale(mu * mu, vi);
+    v[i] = rscale(mu, vi) - rscale(lr, gi);
+}
+}  // namespace
+
+extern "C" int nq_nesterov(nq_ctx_t ctx, void* velocity, const void* dw, int64_t n, nq_dtype dtype, double lr, double mu, void* delta) {
+    if (!ctx || !velocity || !dw || !delta || n <= 0) return NQ_ERR_ARG;
+    if (!nq_is_device_ptr(velocity) || !nq_is_device_ptr(dw) || !nq_is_device_ptr(delta)) return nq_fail(ctx, NQ_ERR_ARG, "nq_nesterov works on device vectors");
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const unsigned g = (unsigned)((n + 255) / 256);
+    switch (dtype) {
+        case NQ_F32: NQ_LAUNCH(ctx, nesterov_kernel<float>, g, 256, 0, (float*)velocity, (const float*)dw, (float*)delta, (float)lr, (float)mu, n); break;
+        case NQ_F64: NQ_LAUNCH(ctx, nesterov_kernel<double>, g, 256, 0, (double*)velocity, (const double*)dw, (double*)delta, lr, mu, n); break;
+        case NQ_C64: NQ_LAUNCH(ctx, nesterov_kernel<cxf>, g, 256, 0, (cxf*)velocity, (const cxf*)dw, (cxf*)delta, (float)lr, (float)mu, n); break;
+        default: NQ_LAUNCH(ctx, nesterov_kernel<cxd>, g, 256, 0, (cxd*)velocity, (const cxd*)dw, (cxd*)delta, lr, mu, n); break;
+    }
+    return NQ_OK;
 }
 
 extern "C" int nq_update(nq_machine_t m, const void* dw, double eta) {

@@ -127,6 +127,9 @@ _PROTOS = {
                                    C.POINTER(_i64)]),
     "nq_sr_solve_matfree_algo": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i32, _dbl, _i32, _dbl, _i64, _vp,
                                         C.POINTER(_i64)]),
+    "nq_sr_accumulate": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _i32]),
+    "nq_sr_finish": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32]),
+    "nq_nesterov": (_i32, [_vp, _vp, _vp, _i64, _i32, _dbl, _dbl, _vp]),
     "nq_update": (_i32, [_vp, _vp, _dbl]),
     "nq_stat_analysis": (_i32, [_vp, _vp, _i64, _i64, _i32, C.POINTER(_dbl)]),
     "nq_abs2": (_i32, [_vp, _vp, _i64, _i32, _vp]),

@@ -103,7 +103,7 @@ class Descent:
         self.eta = eta
 
 
-    def step(self, dw, state=None):
+    def step(self, dw, state=None, ctx=None):
         """(delta, eta) such that w <- w - eta * delta."""
         return dw, self.eta
 
@@ -111,21 +111,33 @@ class Descent:
 class Nesterov:
     """Optimisers.Nesterov(lr, mu) (rules.jl:36-55): v is the velocity kept per parameter vector,
         d = mu^2 v - (1 + mu) lr dw;   v <- mu v - lr dw;   w <- w + d.
-    The velocity lives with the optimiser object (the reference keys an IdDict by the parameter array)."""
+    The velocity lives with the optimiser object (the reference keys an IdDict by the parameter array) as a device vector;
+    the step is one libnqcuda kernel (nq_nesterov)."""
 
     def __init__(self, lr=0.1, mu=0.9, gclip=0.0):
         self.lr, self.mu, self.gclip = float(lr), float(mu), float(gclip)
         self.eta = 1.0
         self.v = None
+        self.delta = None
 
-    def step(self, dw, state=None):
-        if self.v is None or self.v.shape != dw.shape:
-            self.v = dw * 0
-        d = (self.mu ** 2) * self.v - (1.0 + self.mu) * self.lr * dw
-        self.v = self.mu * self.v - self.lr * dw
-        return -d, 1.0                      # w <- w - 1 * (-d)
+    def step(self, dw, state=None, ctx=None):
+        """dw: device tensor.  Returns (delta, 1.0) with w <- w - delta."""
+        import torch
+        if self.v is None or self.v.shape != dw.shape or self.v.dtype != dw.dtype:
+            self.v = torch.zeros_like(dw)
+            self.delta = torch.zeros_like(dw)
+        dw = dw.contiguous()
+        code = {torch.float32: L.NQ_F32, torch.float64: L.NQ_F64, torch.complex64: L.NQ_C64, torch.complex128: L.NQ_C128}[dw.dtype]
+        L.check(L.lib.nq_nesterov(ctx.h, self.v.data_ptr(), dw.data_ptr(), dw.numel(), code, self.lr, self.mu,
+                                  self.delta.data_ptr()), ctx.h)
+        return self.delta, 1.0
 
 
 def update_(opt, net, dw):
-    delta, eta = opt.step(np.asarray(dw))
+    """Optimisers.update!(opt, net, dw) with a host or device dw."""
+    if isinstance(opt, Nesterov) and isinstance(dw, np.ndarray):
+        import torch
+        with torch.cuda.stream(net.ctx.torch_stream()):
+            dw = torch.as_tensor(np.ascontiguousarray(dw, dtype=net.dtype), device=torch.device("cuda", net.ctx.device))
+    delta, eta = opt.step(dw, ctx=net.ctx)
     net.update(delta, eta)

@@ -257,7 +257,7 @@ class BatchedSampler:
         dw = self.dw if dw is None else dw
         net = self.net
         with _torch().cuda.stream(self.ctx.torch_stream()):
-            delta, eta = opt.step(dw)           # Descent: (dw, eta); Nesterov: velocity update on the device tensor
+            delta, eta = opt.step(dw, ctx=self.ctx)     # Descent: (dw, eta); Nesterov: velocity kernel on the device vectors
             if delta.dtype != _tdtype(net.dtype):
                 delta = delta.to(_tdtype(net.dtype))
             delta = delta.contiguous()

@@ -383,3 +383,40 @@ def test_stat_analysis(nq, ctx, dtype):
     tol = 1e-5 if np.dtype(dtype) == np.complex64 else 1e-12
     for a, b in ((m.mean, r["mean"]), (m.error, r["error"]), (m.variance, r["variance"]), (m.tau, r["tau"]), (m.R, r["R"])):
         assert abs(a - b) <= tol * max(1.0, abs(b))
+
+
+@pytest.mark.parametrize("dtype,P,Ns,real_params,chunks", [
+    (np.complex128, 230, 3000, False, (1000, 1000, 1000)), (np.complex128, 576, 2100, True, (512, 1024, 564)),
+    (np.float64, 130, 900, True, (900,)), (np.complex64, 256, 4096, False, (2048, 2048)), (np.complex128, 140, 5000, True, (4096, 904))])
+def test_streaming_sr_assembly(nq, ctx, dtype, P, Ns, real_params, chunks):
+    """nq_sr_accumulate / nq_sr_finish (O produced and consumed chunk by chunk, algebraic centring) reproduce the S of
+    centre + setup on the whole batch: vs the oracle at the stated tolerance, with a mean of the order of the fluctuations
+    (the cancellation case of the algebraic centring)."""
+    L = nq._lib
+    rng = np.random.default_rng(17)
+    dtype = np.dtype(dtype)
+    tol = H.TOL[dtype]
+    O = _rand(rng, (P, Ns), dtype) + dtype.type(1.5)
+    if dtype.kind == "c" and real_params:
+        O[: P // 3] = O[: P // 3].real                       # purely real / purely imaginary row blocks (zero-plane skipping)
+        O[P // 3: 2 * P // 3] = 1j * O[P // 3: 2 * P // 3].imag
+    O64 = O.astype(np.complex128 if dtype.kind == "c" else np.float64)
+    single = dtype in (np.dtype(np.float32), np.dtype(np.complex64))
+    sdt = np.dtype(dtype if (dtype.kind == "c" and not real_params) else (np.float32 if single else np.float64))
+    tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64, np.dtype(np.complex64): torch.complex64,
+           np.dtype(np.complex128): torch.complex128}
+    S = torch.zeros((P, P), dtype=tdt[sdt], device="cuda")
+    sumO = torch.zeros(2 * P, dtype=torch.complex128, device="cuda")
+    assert sum(chunks) == Ns
+    c0 = 0
+    buf = torch.zeros((max(chunks), P), dtype=tdt[dtype], device="cuda")          # ONE reused chunk buffer
+    for i, n in enumerate(chunks):
+        buf[:n].copy_(_dev(O[:, c0:c0 + n]))
+        L.check(L.lib.nq_sr_accumulate(ctx.h, buf.data_ptr(), P, P, n, Ns, L.nq_dtype(dtype), int(real_params), S.data_ptr(),
+                                       sumO.data_ptr(), int(i == 0)), ctx.h)
+        c0 += n
+    L.check(L.lib.nq_sr_finish(ctx.h, S.data_ptr(), sumO.data_ptr(), P, Ns, L.nq_dtype(dtype), int(real_params)), ctx.h)
+    _, rOc = OSR.center(O64)
+    rS, _ = OSR.sr_setup(rOc, np.zeros(P, np.complex128), real_params)
+    H.assert_close(S.cpu().numpy().T, rS, tol, "streamed S")
+    H.assert_close(sumO.cpu().numpy()[:P], O64.mean(axis=1), 1e-13, "<O>")
