@@ -687,6 +687,170 @@ int run_sampler_rule(nq_sampler_t s, const RunArgs& a) {
     }
 }
 
+// NDM with the tracked f' values in REGISTERS (N <= 64 sites: the configuration is two 64-bit registers; M <= 32 KM
+// hidden units and A <= 32 KA ancillas): lane l owns lambda units l + 32 u of BOTH sides and ancillas l + 32 u.  Same
+// recurrence as sampler_ndm_kernel; the factors and numerators of the current proposal stay in registers, so an accepted
+// move re-reads nothing and the reciprocals skip the slow path (fast_rcp).
+template <typename T, int ACT, int KM, int KA>
+__global__ void __launch_bounds__(256) sampler_ndm_reg_kernel(const T* __restrict__ par, const T* __restrict__ tabr,
+                                                               const cx<T>* __restrict__ tabc, uint64_t* __restrict__ st_row,
+                                                               uint64_t* __restrict__ st_col, RunArgs a) {
+    typedef cx<T> C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int64_t chain = blockIdx.x * (int64_t)wpb + warp;
+    const int N = a.N, M = a.M, A = a.A;
+    const int64_t MN = (int64_t)M * N, AN = (int64_t)A * N;
+    const int64_t o_wmu = N + M, o_umu = o_wmu + MN, o_blam = o_umu + AN,
+                  o_hlam = o_blam + N, o_dlam = o_hlam + M, o_wlam = o_dlam + A, o_ulam = o_wlam + MN;
+    T* eb = (T*)smem_raw;                                       // eb[sign * N + j] = exp(dv b_lam_j)
+    for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) {
+        const int sgn = i / N, jj = i - sgn * N;
+        const T dvv = a.hilb == NQ_SPIN ? (sgn ? T(-2) : T(2)) : (sgn ? T(-1) : T(1));
+        eb[i] = (T)exp((double)(dvv * par[o_blam + jj]));
+    }
+    __syncthreads();
+    if (chain >= a.B) return;
+    T* vsw = (T*)(smem_raw + ((size_t)2 * N * sizeof(T) + 15) / 16 * 16) + (size_t)warp * 2 * N;
+    const T half = T(0.5);
+    uint64_t rb = st_row[chain], cb = st_col[chain];
+    unsigned nacc = 0;
+    const int nsteps = a.burn + a.L;
+    T slr[KM], slc[KM];
+    C spi[KA];
+    for (int step = 0; step < nsteps; step++) {
+        if (step % REFRESH_STEPS == 0) {
+            for (int i = lane; i < 2 * N; i += 32) vsw[i] = digit_value<T>(a.hilb, (int)(((i < N ? rb : cb) >> (i < N ? i : i - N)) & 1ull));
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < KM; u++) {
+                const int k = lane + 32 * u;
+                T t = T(0), tp = T(0);
+                if (k < M) {
+                    const T* __restrict__ w = par + o_wlam + k;
+                    t = tp = par[o_hlam + k];
+                    for (int j = 0; j < N; j++) {
+                        const T wv = w[(int64_t)M * j];
+                        t += wv * vsw[j];
+                        tp += wv * vsw[N + j];
+                    }
+                }
+                T f, d, fp, dp;
+                act_eval<ACT>(t, f, d);
+                act_eval<ACT>(tp, fp, dp);
+                slr[u] = d; slc[u] = dp;
+            }
+#pragma unroll
+            for (int u = 0; u < KA; u++) {
+                const int q = lane + 32 * u;
+                T pr = T(0), pim = T(0);
+                if (q < A) {
+                    pr = par[o_dlam + q];
+                    for (int j = 0; j < N; j++) {
+                        const T x = vsw[j], y = vsw[N + j];
+                        pr += half * par[o_ulam + q + (int64_t)A * j] * (x + y);
+                        pim += half * par[o_umu + q + (int64_t)A * j] * (x - y);
+                    }
+                }
+                C f, d;
+                act_eval<ACT>(C(pr, pim), f, d);
+                spi[u] = d;
+            }
+            __syncwarp();
+        }
+        DrawBatch<T> db;
+#pragma unroll 1
+        for (int ps = 0; ps < a.passes; ps++) {
+            const int pic = step * a.passes + ps;
+            if ((ps & 31) == 0) db.fill(a, chain, pic, a.passes - ps, a.diag ? N : 2 * N, lane);
+            int site; T u01;
+            db.get(ps & 31, site, u01);
+            const bool col = !a.diag && site >= N;
+            const int j = col ? site - N : site;
+            const int bit = (int)(((col ? cb : rb) >> j) & 1ull);
+            const int sg = bit;                                     // digit 0 -> the value increases (sign 0), 1 -> decreases
+            const T* __restrict__ tp = tabr + (int64_t)sg * 2 * MN + (int64_t)M * j + lane;          // lambda layer = lay 0
+            const T* __restrict__ tm = tabr + (int64_t)(1 - sg) * 2 * MN + (int64_t)M * j + lane;
+            const C* __restrict__ cp = tabc + (int64_t)sg * AN + (int64_t)A * j + lane;
+            const C* __restrict__ cm = tabc + (int64_t)(1 - sg) * AN + (int64_t)A * j + lane;
+            T facl[KM], numl[KM];
+            C facp[KA], nump[KA];
+            double pl = 1.0;
+#pragma unroll
+            for (int u = 0; u < KM; u++) {
+                const bool on = lane + 32 * u < M;
+                const T Ep = on ? tp[32 * u] : T(1), Em = (ACT == NQ_LOGCOSH && on) ? tm[32 * u] : T(1);
+                ratio_parts<ACT>(col ? slc[u] : slr[u], Ep, Em, facl[u], numl[u]);
+                pl *= (double)facl[u];
+            }
+#pragma unroll
+            for (int u = 0; u < KA; u++) {
+                const bool on = lane + 32 * u < A;
+                C Ep = on ? cp[32 * u] : C(T(1), T(0)), Em = (ACT == NQ_LOGCOSH && on) ? cm[32 * u] : C(T(1), T(0));
+                if (col) { Ep.im = -Ep.im; Em.im = -Em.im; }
+                if (a.diag) {
+                    Ep = C(Ep.re * Ep.re + Ep.im * Ep.im, T(0));
+                    Em = C(Em.re * Em.re + Em.im * Em.im, T(0));
+                }
+                ratio_parts<ACT>(spi[u], Ep, Em, facp[u], nump[u]);
+                pl *= a.diag ? (double)facp[u].re : abs2_d(facp[u]);
+            }
+            pl = warp_prod(pl);
+            const double pr = pl * (double)eb[sg * N + j];
+            const bool acc = (u01 - (T)pr) < T(0);
+            if (acc) {
+#pragma unroll
+                for (int u = 0; u < KM; u++) {
+                    const T sn = q_div(numl[u], ACT == NQ_SOFTPLUS ? facl[u] : T(2) * facl[u]);
+                    if (col) slc[u] = sn; else slr[u] = sn;
+                    if (a.diag) slc[u] = sn;
+                }
+#pragma unroll
+                for (int u = 0; u < KA; u++) spi[u] = q_div(nump[u], ACT == NQ_SOFTPLUS ? facp[u] : rscale(T(2), facp[u]));
+                if (col || a.diag) cb ^= 1ull << j;
+                if (!col) rb ^= 1ull << j;
+                nacc++;
+            }
+            if (a.replay && a.accept_out && lane == 0) a.accept_out[(int64_t)pic * a.B + chain] = acc ? 1 : 0;
+        }
+        if (step >= a.burn && a.out_prow && lane == 0) {
+            const int64_t o = (int64_t)(step - a.burn) * a.B + chain;
+            a.out_prow[o] = rb;
+            if (a.out_pcol) a.out_pcol[o] = cb;
+        }
+    }
+    if (lane == 0) {
+        st_row[chain] = rb; st_col[chain] = cb;
+        if (nacc) atomicAdd(a.accepted, (unsigned long long)nacc);
+    }
+}
+
+template <typename T, int ACT, int KM, int KA>
+int launch_sampler_ndm_reg(nq_sampler_t s, const RunArgs& a) {
+    nq_machine_t m = s->m;
+    nq_ctx_t ctx = m->ctx;
+    const int wpb = 8;
+    const size_t smem = ((size_t)2 * m->N * sizeof(T) + 15) / 16 * 16 + (size_t)wpb * 2 * m->N * sizeof(T);
+    const cx<T>* tabc = (const cx<T>*)((const char*)m->etab + ((size_t)4 * m->M * m->N * sizeof(T) + 15) / 16 * 16);
+    auto kern = sampler_ndm_reg_kernel<T, ACT, KM, KA>;
+    unsigned grid = (unsigned)((s->B + wpb - 1) / wpb);
+    NQ_LAUNCH(ctx, kern, grid, wpb * 32, smem, (const T*)m->params, (const T*)m->etab, tabc, s->prow, s->pcol, a);
+    return NQ_OK;
+}
+
+// M, A <= 64 and N <= 64: the register kernel; returns false when the shape needs the shared-memory kernel
+template <typename T, int ACT>
+bool try_sampler_ndm_reg(nq_sampler_t s, const RunArgs& a, int* status) {
+    nq_machine_t m = s->m;
+    if (m->N > 64 || m->M > 64 || m->A > 64) return false;
+    const int km = m->M <= 32 ? 1 : 2, ka = m->A <= 32 ? 1 : 2;
+    if (km == 1 && ka == 1) *status = launch_sampler_ndm_reg<T, ACT, 1, 1>(s, a);
+    else if (km == 1) *status = launch_sampler_ndm_reg<T, ACT, 1, 2>(s, a);
+    else if (ka == 1) *status = launch_sampler_ndm_reg<T, ACT, 2, 1>(s, a);
+    else *status = launch_sampler_ndm_reg<T, ACT, 2, 2>(s, a);
+    return true;
+}
+
 template <typename E, int ACT, bool DOUBLED, int KU>
 int launch_sampler_rbm_ku(nq_sampler_t s, const RunArgs& a) {
     typedef typename elem_traits<E>::real T;
@@ -721,6 +885,9 @@ template <typename T, int ACT>
 int launch_sampler_ndm(nq_sampler_t s, const RunArgs& a) {
     nq_machine_t m = s->m;
     nq_ctx_t ctx = m->ctx;
+    static const bool smem_only = [] { const char* e = getenv("NQ_SAMPLER_NDM"); return e && !strcmp(e, "smem"); }();
+    int st = NQ_OK;
+    if (!smem_only && try_sampler_ndm_reg<T, ACT>(s, a, &st)) return st;
     size_t per_warp = ((size_t)(4 * m->M + 2 * m->N) * sizeof(T) + (size_t)3 * m->A * sizeof(cx<T>) + 15) / 16 * 16;
     const size_t tab_bytes = ((size_t)2 * m->N * sizeof(T) + 15) / 16 * 16;
     const cx<T>* tabc = (const cx<T>*)((const char*)m->etab + ((size_t)4 * m->M * m->N * sizeof(T) + 15) / 16 * 16);
