@@ -374,8 +374,7 @@ def run_gpu(args):
 
     # ---- e2e: public API with HOST buffers (pinned), H2D of the configurations and D2H of L_loc inside ----
     def e2e_step():
-        bs.set_samples(sig)
-        bs.evaluate()
+        bs.evaluate_host(sig)          # set_samples + evaluate, copies of piece c+1 overlapped with the kernel on piece c
         host_loc.copy_(bs.loc, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     e2e_step()

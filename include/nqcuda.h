@@ -286,6 +286,12 @@ int nq_force_liouvillian(nq_ctx_t ctx, const void* Lloc, const void* gLloc, int6
  * ref: SR/SRDirect.jl:26-49, SRIterative.jl:45-62 */
 int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total,
                 nq_dtype dtype, const void* gradC, int real_params, void* S, void* F);
+/* One-shot structural hint for the NEXT nq_sr_setup on this context: row_planes [P] host bytes, bit 0 = the real part of
+ * the row may be non-zero, bit 1 = the imaginary part may be.  For the real-parameter NDM the gradient rows of the lambda
+ * biases / weights are purely real and those of the mu biases / weights purely imaginary (NDMBatched.jl:262-277); with
+ * the hint the assembly skips those operand planes without scanning O for them (it scans when no hint is given).  A hint
+ * that clears a plane which is not identically zero gives a wrong S.  NULL clears the hint. */
+int nq_sr_hint_row_planes(nq_ctx_t ctx, const uint8_t* row_planes, int64_t P);
 /* (S + eps I) dw = F.  sdtype = element type of S/F/dw (real or complex).  S is overwritten.
  * CHOLESKY: NQ_ERR_NOT_POSDEF if a pivot <= 0.  CG: IterativeSolvers-0.8.1 semantics, x0 = 0,
  * stop ||r|| <= tol ||F||, maxiter (<=0: 10 P); NQ_ERR_NOT_CONVERGED when exhausted.

@@ -522,6 +522,9 @@ end
 sr_finish!(ctx::Ctx, Sacc, sumO, P::Integer, Ns_total::Integer, T::Type, real_params::Bool) =
     check(ctx, ccall((:nq_sr_finish, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Cint, Cint),
                      ctx.h, Sacc, sumO, P, Ns_total, nqdtype(T), real_params ? 1 : 0))
+# structure of the gradient rows known to the caller (NDM: lambda rows real, mu rows imaginary): one-shot hint for the next setup
+sr_hint_row_planes!(ctx::Ctx, planes::Vector{UInt8}) =
+    check(ctx, ccall((:nq_sr_hint_row_planes, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), ctx.h, planes, length(planes)))
 # Optimisers.apply(o::Nesterov, x, Δ, state) on device vectors (rules.jl:44-55): returns -d in `delta`
 nesterov!(ctx::Ctx, delta, velocity, Δ, n::Integer, T::Type, o) =
     check(ctx, ccall((:nq_nesterov, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Cdouble, Cdouble, Ptr{Cvoid}),

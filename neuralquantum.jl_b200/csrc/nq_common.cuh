@@ -30,6 +30,10 @@ struct nq_ctx_s {
     void* nccl_comm = nullptr;
     int nranks = 1, rank = 0;
     int64_t ns_total = 0;          // global sample count override (nq_comm_set_global_samples), 0 = Ns * nranks
+    // one-shot structural hint for the next nq_sr_setup (nq_sr_hint_row_planes): per 128-row tile, which component planes
+    // of O may be non-zero (bit 0 = re, bit 1 = im); replaces the scan of O by tile_activity_kernel
+    std::vector<unsigned> hint_tile_flags;
+    int64_t hint_P = 0;
 };
 
 int nq_fail(nq_ctx_t ctx, int code, const char* fmt, ...);

@@ -637,9 +637,14 @@ int launch_syrk(nq_ctx_t ctx, const void* X, int64_t ldr, int64_t P, int64_t Ns,
     if (!flags) return NQ_ERR_ALLOC;
     int* order = NC == 2 ? (int*)(flags + ntile) : nullptr;
     if (NC == 2 && mode == 0) {       // mode 1 (same launch sequence) reuses the flags
-        NQ_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)ntile * sizeof(unsigned), ctx->stream));
-        dim3 g((unsigned)((P * NC + 255) / 256), (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, Ns / 64)));
-        NQ_LAUNCH(ctx, (tile_activity_kernel<T, NC>), g, 256, 0, (const T*)X, ldr, P, Ns, flags);
+        if (ctx->hint_P == P && (int)ctx->hint_tile_flags.size() == ntile) {
+            // the caller knows the structure of the rows (nq_sr_hint_row_planes): no pass over O
+            NQ_CUDA(ctx, cudaMemcpyAsync(flags, ctx->hint_tile_flags.data(), (size_t)ntile * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            NQ_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)ntile * sizeof(unsigned), ctx->stream));
+            dim3 g((unsigned)((P * NC + 255) / 256), (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, Ns / 64)));
+            NQ_LAUNCH(ctx, (tile_activity_kernel<T, NC>), g, 256, 0, (const T*)X, ldr, P, Ns, flags);
+        }
     }
     if (NC == 2) NQ_LAUNCH(ctx, tile_order_kernel, 1, 256, 0, (const unsigned*)flags, ntile, mode, order);
     dim3 grid((unsigned)ntri, (unsigned)nsplit);
@@ -1972,6 +1977,18 @@ extern "C" int nq_force_liouvillian(nq_ctx_t ctx, const void* Lloc, const void* 
     return st.finish();
 }
 
+extern "C" int nq_sr_hint_row_planes(nq_ctx_t ctx, const uint8_t* row_planes, int64_t P) {
+    if (!ctx || P < 0) return NQ_ERR_ARG;
+    ctx->hint_P = 0;
+    ctx->hint_tile_flags.clear();
+    if (!row_planes || P == 0) return NQ_OK;
+    const int64_t ntile = (P + TS - 1) / TS;
+    ctx->hint_tile_flags.assign((size_t)ntile, 0u);
+    for (int64_t k = 0; k < P; k++) ctx->hint_tile_flags[(size_t)(k / TS)] |= (unsigned)(row_planes[k] & 3);
+    ctx->hint_P = P;
+    return NQ_OK;
+}
+
 extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total,
                            nq_dtype dtype, const void* gradC, int real_params, void* S, void* F) {
     if (!ctx || !Oc || !gradC || !S || !F || P <= 0 || Ns <= 0 || ldO < P || Ns_total < Ns) return NQ_ERR_ARG;
@@ -2037,6 +2054,7 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
     else
         NQ_LAUNCH(ctx, syrk_finalize_kernel<float>, grid, 128, 0, (const double*)Wre, (const double*)Wim, nsplit, Ppad, P, scale, (int)out_complex, (float*)dS);
     }
+    ctx->hint_P = 0;                       // the structural hint is one-shot
     // F = gradC (complex nets) or Re(gradC)
     cxd* tmp = (cxd*)nq_scratch(ctx, SL_W2, (size_t)P * sizeof(cxd));
     if (!tmp) return NQ_ERR_ALLOC;

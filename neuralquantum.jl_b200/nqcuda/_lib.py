@@ -121,6 +121,7 @@ _PROTOS = {
     "nq_force_ket": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),
     "nq_force_liouvillian": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, C.POINTER(_dbl)]),
     "nq_sr_setup": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i32, _vp, _vp]),
+    "nq_sr_hint_row_planes": (_i32, [_vp, _vp, _i64]),
     "nq_sr_solve": (_i32, [_vp, _vp, _vp, _i64, _i32, _dbl, _i32, _dbl, _i64, _vp, C.POINTER(_i64)]),
     "nq_sr_scale_diagonal": (_i32, [_vp, _vp, _i64, _i32, _dbl]),
     "nq_sr_solve_matfree": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i32, _dbl, _dbl, _i64, _vp,

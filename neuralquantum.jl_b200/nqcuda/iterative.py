@@ -89,6 +89,14 @@ class BatchedSampler:
         self.F = torch.zeros(P, dtype=st, device=dev)
         self.dw = torch.zeros(P, dtype=st, device=dev)
         self.abs2 = torch.zeros(Ns, dtype=_tdtype(net.rdtype), device=dev) if self.is_liouvillian else None
+        # structure of the gradient rows of the real-parameter NDM (NDMBatched.jl:262-277): b/h/w of mu purely imaginary,
+        # b/h/w of lambda purely real, the ancilla fields complex -> the S assembly skips the zero planes without scanning O
+        self.row_planes = None
+        if net.kind == L.NQ_NDM:
+            planes = {"b_mu": 2, "h_mu": 2, "w_mu": 2, "u_mu": 3, "b_lam": 1, "h_lam": 1, "d_lam": 3, "w_lam": 1, "u_lam": 3}
+            self.row_planes = np.concatenate([np.full(int(np.prod(shp)), planes[f], dtype=np.uint8)
+                                              for f, shp in zip(net.fields, net.shapes)])
+            assert self.row_planes.size == P
         self.cost = None
         self.last_iters = 0
 
@@ -130,6 +138,49 @@ class BatchedSampler:
         L.check(L.lib.nq_logpsi_grad_local_packed(net.h, self.op.h, self.prow.data_ptr(), pc, Ns, self.logpsi.data_ptr(),
                                                   self.O.data_ptr(), net.P, self.loc.data_ptr(), gl, net.P), ctx.h)
 
+    def evaluate_host(self, sigma, chunks=2):
+        """set_samples + evaluate for HOST configurations [N, B, L] (pinned memory makes the copies asynchronous), software
+        pipelined: the batch is cut into `chunks` pieces; the float arrays of piece c+1 are copied on a side stream while the
+        fused kernel works on piece c (the kernel is persistent and fills every SM, so only the copy engine overlaps; the
+        two small packing kernels of a piece run between two fused launches).  Same results as set_samples(sigma);
+        evaluate() -- every copy still happens inside the call."""
+        from .core import Context
+        torch = _torch()
+        net, ctx, Ns, P = self.net, self.ctx, self.Ns, self.net.P
+        if self.symm or chunks <= 1 or Ns < 4096 * chunks:
+            self.set_samples(sigma)
+            return self.evaluate()
+        dev = torch.device("cuda", ctx.device)
+        sr, sc = sigma if net.doubled else (sigma, None)
+        hosts = [torch.from_numpy(np.asfortranarray(a).reshape(net.N, Ns, order="F").T) for a in (sr, sc) if a is not None]
+        if getattr(self, "_side", None) is None or self._side[2].dtype != hosts[0].dtype:
+            st = torch.cuda.Stream(device=dev)
+            self._side = (st, Context(ctx.device, st.cuda_stream), torch.empty((2, Ns, net.N), dtype=hosts[0].dtype, device=dev))
+        side_stream, side_ctx, stage = self._side
+        main_stream = ctx.torch_stream()
+        bufs = [self.prow, self.pcol][:len(hosts)]
+        W = self.prow.shape[-1]
+        es, cs = self.O.element_size(), self.loc.element_size()
+        fcode = L.nq_dtype(np.dtype(str(hosts[0].dtype).replace("torch.", "")))
+        bounds = [(Ns * c) // chunks for c in range(chunks + 1)]
+        side_stream.wait_stream(main_stream)                       # the staging / packed buffers may still be read by earlier work
+        for c in range(chunks):
+            c0, n = bounds[c], bounds[c + 1] - bounds[c]
+            with torch.cuda.stream(side_stream):
+                for i, h in enumerate(hosts):
+                    stage[i, c0:c0 + n].copy_(h[c0:c0 + n], non_blocking=True)
+            for i, buf in enumerate(bufs):
+                L.check(L.lib.nq_pack_states(side_ctx.h, net.hilb.code, net.N, n, stage[i, c0:c0 + n].data_ptr(), fcode,
+                                             buf.data_ptr() + c0 * W * 8), side_ctx.h)
+            ev = torch.cuda.Event()
+            ev.record(side_stream)
+            main_stream.wait_event(ev)
+            pc = self.pcol.data_ptr() + c0 * W * 8 if self.pcol is not None else None
+            gl = self.gloc.data_ptr() + c0 * P * cs if self.is_liouvillian else None
+            L.check(L.lib.nq_logpsi_grad_local_packed(net.h, self.op.h, self.prow.data_ptr() + c0 * W * 8, pc, n,
+                                                      self.logpsi.data_ptr() + c0 * es, self.O.data_ptr() + c0 * P * es, P,
+                                                      self.loc.data_ptr() + c0 * cs, gl, P), ctx.h)
+
     def assemble(self):
         """centre O, force vector, SR setup (S, F)."""
         net, ctx, Ns, P = self.net, self.ctx, self.Ns, self.net.P
@@ -146,6 +197,8 @@ class BatchedSampler:
             L.check(L.lib.nq_force_ket(ctx.h, self.O.data_ptr(), P, P, Ns, oc, self.loc.data_ptr(),
                                        self.gradC.data_ptr()), ctx.h)
         if self.S is not None:
+            if self.row_planes is not None:
+                L.check(L.lib.nq_sr_hint_row_planes(ctx.h, L.ptr(self.row_planes), P), ctx.h)
             L.check(L.lib.nq_sr_setup(ctx.h, self.O.data_ptr(), P, P, Ns, self.Ns_total, oc, self.gradC.data_ptr(),
                                       int(self.real_params), self.S.data_ptr(), self.F.data_ptr()), ctx.h)
             if self.nranks > 1:      # C4 (global mean, quirk Q5)

@@ -128,3 +128,27 @@ def test_sampler_independent_of_sharding(nq, ctx):
         assert torch.equal(pr, rows[:, r * half:(r + 1) * half])
         assert torch.equal(pc, cols[:, r * half:(r + 1) * half])
     assert int((rows != 0).sum()) > 0
+
+
+def test_pipelined_host_evaluate_is_bit_identical(nq, ctx):
+    """BatchedSampler.evaluate_host (copies and packing of piece c+1 on a side stream while the fused kernel works on piece c)
+    gives exactly the arrays of set_samples + evaluate."""
+    import torch
+    N, B, Lc = 8, 2048, 8
+    om, pm, hilb = H.make_pair(nq, ctx, "ndm", "fock", N, 2, np.float64, 0, seed=4, std=0.2)
+    _, _, _, pl = H.p_lindblad_ising_1d(nq, N)
+    bs = nq.BatchedSampler(pm, nq.MetropolisSampler(nq.LocalRule(), Lc, N, burn=1, seed=1), pl, nq.SR(np.float32, eps=0.001), batch_sz=B)
+    Ns = B * Lc
+    hr = torch.from_numpy(H.rand_states("fock", N, Ns, 11).T.copy()).pin_memory()
+    hc = torch.from_numpy(H.rand_states("fock", N, Ns, 12).T.copy()).pin_memory()
+    sig = (hr.numpy().T.reshape(N, B, Lc, order="F"), hc.numpy().T.reshape(N, B, Lc, order="F"))
+    bs.set_samples(sig)
+    bs.evaluate()
+    torch.cuda.synchronize()
+    ref = [t.clone() for t in (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc)]
+    for t in (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc):
+        t.zero_()
+    bs.evaluate_host(sig, chunks=4)
+    torch.cuda.synchronize()
+    for a, b in zip(ref, (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc)):
+        assert torch.equal(a, b)
