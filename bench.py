@@ -113,7 +113,7 @@ def ncu_fused_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused kernel on the cfg4 batch, taken from the
     committed `ncu --set full` capture (profiles/ncu_traffic.py writes the file); None when the file is absent."""
     try:
-        rec = json.load(open(os.path.join(ROOT, "profiles", "r2c_fused_kernel_traffic.json")))
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r2m_fused_kernel_traffic.json")))
         return float(rec["dram_bytes"]), rec.get("report")
     except Exception:
         return None, None
