@@ -1126,7 +1126,9 @@ __global__ void __launch_bounds__(256) chol_fused_kernel(E* __restrict__ A, int6
         const int64_t base = j0 + nb, below = P - base;
         if (below <= 0) break;
         // ---- panel: the CTAs that own rows below the block load the factored block and y_blk, then TRSM their rows
-        const bool has_rows = (int64_t)blockIdx.x * 256 < below;
+        // rows are dealt round-robin to ALL CTAs (row = base + CTA + nblocks * thread): with contiguous blocks of 256 rows only
+        // below / 256 CTAs worked while the others waited at the barrier (cfg3: 21 of 148, 41 us per step)
+        const bool has_rows = (int64_t)blockIdx.x < below;
         if (has_rows) {
             for (int i = tid; i < NB * NB; i += 256) {
                 const int r = i % NB, c = i / NB;
@@ -1137,7 +1139,7 @@ __global__ void __launch_bounds__(256) chol_fused_kernel(E* __restrict__ A, int6
             if (tid < NB) Dinv[tid] = tid < nb ? 1.0 / real_part(Lb[tid][tid]) : 1.0;
             __syncthreads();
             tick(0);
-            const int64_t row = base + (int64_t)blockIdx.x * 256 + tid;
+            const int64_t row = base + (int64_t)blockIdx.x + (int64_t)nblocks * tid;
             if (row < P) {
                 E xr[NB];
 #pragma unroll
@@ -1196,23 +1198,23 @@ __global__ void __launch_bounds__(256) chol_fused_kernel(E* __restrict__ A, int6
                 while ((int64_t)bi * (bi + 1) / 2 > t) bi--;
                 const int bj = (int)(t - (int64_t)bi * (bi + 1) / 2);
                 const int64_t i0 = base + (int64_t)bi * 32, l0 = base + (int64_t)bj * 32;
-                // the C tile is read-modified-written once, after the k loop, and usually comes from HBM (the trailing matrix
-                // does not fit in L2): start those lines moving now so that the epilogue finds them in L2
-                {
-                    constexpr int LPC = CPLX ? 4 : 2;                // 128-byte lines per 32-row column segment
-                    for (int q = lane; q < 32 * LPC; q += 32) {
-                        const int64_t col = l0 + q / LPC, row = i0 + (q % LPC) * (32 / LPC);
-                        if (row < P && col < P) asm volatile("prefetch.global.L2 [%0];" ::"l"(Ad + (row + P * col) * NPL));
-                    }
-                }
+                // C_new = C_old - A B^H: the accumulators START from the C tile (all its loads are issued here, in flight
+                // together with the operand fragments) and the A fragments are negated, so the epilogue is a pure store.
+                // The first version read-modified-wrote the tile after the k loop: 30 % of the kernel's samples waited on
+                // those loads (profiles/r2n_chol_c128_lines_before.txt).
                 double cre[4][4][2], cim[CPLX ? 4 : 1][CPLX ? 4 : 1][2];
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        cre[i][j][0] = cre[i][j][1] = 0.0;
-                        if (CPLX) cim[i][j][0] = cim[i][j][1] = 0.0;
-                    }
+                    for (int j = 0; j < 4; j++)
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int64_t row = i0 + i * 8 + g, col = l0 + j * 8 + 2 * tq + h;
+                            const bool ok = row < P && col < P && row >= col;
+                            const int64_t at = (row + P * col) * NPL;
+                            cre[i][j][h] = ok ? __ldcg(Ad + at) : 0.0;
+                            if (CPLX) cim[i][j][h] = ok ? __ldcg(Ad + at + 1) : 0.0;
+                        }
 #pragma unroll 1
                 for (int k0 = 0; k0 < NB / 4; k0 += KU) {
                     double ar[KU][4], ai[CPLX ? KU : 1][4], br[KU][4], bi_[CPLX ? KU : 1][4];
@@ -1225,9 +1227,9 @@ __global__ void __launch_bounds__(256) chol_fused_kernel(E* __restrict__ A, int6
                             if (CPLX) {
                                 const double2 va = ra < P ? __ldcg(reinterpret_cast<const double2*>(Ad) + ra + colo) : make_double2(0.0, 0.0);
                                 const double2 vb = rb < P ? __ldcg(reinterpret_cast<const double2*>(Ad) + rb + colo) : make_double2(0.0, 0.0);
-                                ar[u][i] = va.x; ai[u][i] = va.y; br[u][i] = vb.x; bi_[u][i] = vb.y;
+                                ar[u][i] = -va.x; ai[u][i] = -va.y; br[u][i] = vb.x; bi_[u][i] = vb.y;
                             } else {
-                                ar[u][i] = ra < P ? __ldcg(Ad + ra + colo) : 0.0;
+                                ar[u][i] = ra < P ? -__ldcg(Ad + ra + colo) : 0.0;
                                 br[u][i] = rb < P ? __ldcg(Ad + rb + colo) : 0.0;
                             }
                         }
@@ -1255,8 +1257,8 @@ __global__ void __launch_bounds__(256) chol_fused_kernel(E* __restrict__ A, int6
                             const int64_t row = i0 + i * 8 + g, col = l0 + j * 8 + 2 * tq + h;
                             if (row < P && col < P && row >= col) {
                                 const int64_t at = (row + P * col) * NPL;
-                                Aw[at] = __ldcg(Ad + at) - cre[i][j][h];
-                                if (CPLX) Aw[at + 1] = __ldcg(Ad + at + 1) - cim[i][j][h];
+                                Aw[at] = cre[i][j][h];
+                                if (CPLX) Aw[at + 1] = cim[i][j][h];
                             }
                         }
             }
