@@ -15,8 +15,11 @@
 // 4-byte words into the K-major core matrices (8 rows x 16 bytes; LBO = 144 keeps the scatter conflict-free).
 // Thread 0 issues the MMAs (M = N = 128, K = 8); tcgen05.commit releases the stage through an mbarrier while
 // the other threads already convert the next chunk.  2 CTAs per SM overlap one CTA's drain with the other's MMAs.
+// (This staging kernel is the fallback; the default since round 2 is the TMA-fed pipeline at the end of the file.)
 #include "nq_internal.cuh"
 #include <algorithm>
+#include <cuda.h>
+#include <cudaTypedefs.h>
 
 namespace {
 
@@ -324,11 +327,282 @@ int run_tf32(nq_ctx_t ctx, const float* X, int64_t ldr, int64_t P, int64_t Ns, i
     return NQ_OK;
 }
 
+
+// =====================================================================================================================
+// TMA-fed variant (round 2).  The staging kernel above spends its time converting: per 8-sample chunk the 8 warps move
+// 32 KB through registers into shared memory for ~200 tensor cycles (ncu: tensor pipe 23 % active, long-scoreboard 3.0 per
+// issue).  Here the conversion happens ONCE, in a streaming pre-pass that writes the operands the way the tensor core wants
+// them -- K-major (sample-contiguous), component planes de-interleaved, split into tf32 hi / lo -- and the SYRK itself is a
+// warp-specialised TMA + tcgen05 pipeline:
+//   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor 2D boxes of [128 rows x 32 samples] with the 128-byte swizzle
+//                      straight into the UMMA layout, 3 stages of (A_hi, A_lo, B_hi, B_lo) = 64 KB
+//   warp 1 (one lane)  MMA issuer: per stage 4 k-steps x (lo*hi, hi*lo, hi*hi); tcgen05.commit frees the stage
+//   warps 4-7          epilogue: the FP32 accumulation of the tensor core truncates, so a TMEM accumulator only ever holds
+//                      WINS stages (128 samples); two accumulators (2 x 128 columns) alternate, the finished one is drained
+//                      with round-to-nearest adds into 128 registers per thread while the MMAs fill the other
+// The (re, im) planes of complex rows enter as extra K steps (items = (chunk, component)).
+// =====================================================================================================================
+constexpr int KB_T = 32;                 // samples per stage: one 128-byte swizzle row of floats
+constexpr int OPB = TS * KB_T * 4;       // bytes of one operand box
+constexpr int NSTG = 3;
+constexpr int WINS = 4;                  // stages per accumulation window
+
+// out[hl][c][k][s] (s contiguous, k padded to Ppad, s padded to Nspad with zeros) from X[(k NC + c) + ldr s]
+template <int NC>
+__global__ void tf32_split_kernel(const float* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, int64_t Ppad, int64_t Nspad,
+                                  float* __restrict__ out) {
+    __shared__ float tile[32 * NC][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;                    // 32 x 8
+    const int64_t k0 = (int64_t)blockIdx.x * 32, s0 = (int64_t)blockIdx.y * 32;
+    for (int i = ty; i < 32; i += 8) {                               // sample s0 + i, real rows (k0 NC) + tx + 32 j
+        const int64_t smp = s0 + i;
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            const int64_t r = k0 * NC + tx + 32 * j;
+            tile[tx + 32 * j][i] = (smp < Ns && r < P * NC) ? Xr[r + ldr * smp] : 0.f;
+        }
+    }
+    __syncthreads();
+    const size_t plane = (size_t)Ppad * Nspad;
+    for (int i = ty; i < 32; i += 8) {                               // row k0 + i, sample s0 + tx
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const float x = tile[i * NC + c][tx];
+            const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+            const size_t at = (size_t)(k0 + i) * Nspad + (s0 + tx);
+            out[(size_t)c * plane + at] = h;
+            out[(size_t)(NC + c) * plane + at] = x - h;
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    // K-major, 128-byte swizzle: 8-row atoms of 1024 bytes (SBO), LBO unused (1), version 1, layout type 2 = SWIZZLE_128B
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256, 1)
+syrk_tf32_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t Ppad, int64_t Nspad, int ntile, int nsplit, int mode,
+                     const unsigned* __restrict__ tflags, float* __restrict__ Wk /* [nsplit][Ppad*Ppad] */) {
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + NSTG * 4 * OPB);
+    uint64_t* empty = full + NSTG;
+    uint64_t* accfull = empty + NSTG;
+    uint64_t* accempty = accfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    int t = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+    while (ti * (ti + 1) / 2 > t) ti--;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int split = blockIdx.y;
+    const int64_t nchunk_tot = Nspad / KB_T;
+    const int64_t cper = (nchunk_tot + nsplit - 1) / nsplit;
+    const int64_t c_begin = split * cper, c_end = std::min<int64_t>(nchunk_tot, c_begin + cper);
+
+    const unsigned fa = NC == 2 ? tflags[ti] : 1u, fb = NC == 2 ? tflags[tj] : 1u;
+    int comps[2], ncomp = 0;                // K planes of A that are used
+    for (int c = 0; c < NC; c++) {
+        const unsigned bc = mode == 0 ? c : 1 - c;
+        if (((fa >> c) & 1u) && ((fb >> bc) & 1u)) comps[ncomp++] = c;
+    }
+    const bool same = ti == tj && mode == 0;          // B is A itself: one pair of boxes per item
+    const int64_t nit = (c_end > c_begin ? c_end - c_begin : 0) * ncomp;
+    const int64_t nwin = (nit + WINS - 1) / WINS;
+
+    if (tid == 0) {
+        for (int i = 0; i < NSTG; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&accfull[i], 1); mbar_init(&accempty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---- TMA producer
+        const int64_t rowsA = (int64_t)ti * TS, rowsB = (int64_t)tj * TS;
+        for (int64_t it = 0; it < nit; it++) {
+            const int s = (int)(it % NSTG);
+            mbar_wait(&empty[s], (uint32_t)(((it / NSTG) & 1) ^ 1));
+            const int comp = comps[it % ncomp], bcomp = mode == 0 ? comp : 1 - comp;
+            const int32_t k0 = (int32_t)((c_begin + it / ncomp) * KB_T);
+            unsigned char* st = base + (size_t)s * 4 * OPB;
+            mbar_expect_tx(&full[s], same ? 2u * OPB : 4u * OPB);
+            tma_load_2d(st, &tmap, k0, (int32_t)((0 * NC + comp) * Ppad + rowsA), &full[s]);              // A hi
+            tma_load_2d(st + OPB, &tmap, k0, (int32_t)((1 * NC + comp) * Ppad + rowsA), &full[s]);        // A lo
+            if (!same) {
+                tma_load_2d(st + 2 * OPB, &tmap, k0, (int32_t)((0 * NC + bcomp) * Ppad + rowsB), &full[s]);   // B hi
+                tma_load_2d(st + 3 * OPB, &tmap, k0, (int32_t)((1 * NC + bcomp) * Ppad + rowsB), &full[s]);   // B lo
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---- MMA issuer
+        for (int64_t it = 0; it < nit; it++) {
+            const int s = (int)(it % NSTG);
+            const int64_t w = it / WINS;
+            const int b = (int)(w & 1);
+            if (it % WINS == 0) {
+                mbar_wait(&accempty[b], (uint32_t)(((w >> 1) & 1) ^ 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            mbar_wait(&full[s], (uint32_t)((it / NSTG) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int comp = comps[it % ncomp];
+            const uint32_t idesc = make_idesc(mode == 1 && comp == 1);
+            const uint32_t a_hi = smem_u32(base + (size_t)s * 4 * OPB), a_lo = a_hi + OPB;
+            const uint32_t b_hi = same ? a_hi : a_hi + 2 * OPB, b_lo = same ? a_lo : a_hi + 3 * OPB;
+            const uint32_t acc = tmem + (uint32_t)(b * 128);
+#pragma unroll
+            for (int kk = 0; kk < KB_T / KC; kk++) {
+                const uint32_t ko = (uint32_t)(kk * KC * 4);
+                const uint32_t first = (it % WINS == 0 && kk == 0) ? 0u : 1u;
+                mma_tf32(acc, make_desc_sw128(a_lo + ko), make_desc_sw128(b_hi + ko), idesc, first);
+                mma_tf32(acc, make_desc_sw128(a_hi + ko), make_desc_sw128(b_lo + ko), idesc, 1u);
+                mma_tf32(acc, make_desc_sw128(a_hi + ko), make_desc_sw128(b_hi + ko), idesc, 1u);
+            }
+            umma_commit(&empty[s]);                                   // the stage is free once these MMAs have read it
+            if (it % WINS == WINS - 1 || it + 1 == nit) umma_commit(&accfull[b]);
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 (= rows of the tile), all 128 columns
+        float acc[128];
+#pragma unroll
+        for (int i = 0; i < 128; i++) acc[i] = 0.f;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        for (int64_t w = 0; w < nwin; w++) {
+            const int b = (int)(w & 1);
+            mbar_wait(&accfull[b], (uint32_t)((w >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ta = tmem + lane_base + (uint32_t)(b * 128);
+            tmem_add32(ta, acc);
+            tmem_add32(ta + 32, acc + 32);
+            tmem_add32(ta + 64, acc + 64);
+            tmem_add32(ta + 96, acc + 96);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&accempty[b]);
+        }
+        float* W = Wk + (size_t)split * Ppad * Ppad;
+        const int64_t row = (int64_t)ti * TS + (warp & 3) * 32 + lane;
+        const int64_t col0 = (int64_t)tj * TS;
+#pragma unroll
+        for (int i = 0; i < 128; i++) W[row + Ppad * (col0 + i)] = acc[i];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256u) : "memory");
+}
+
+template <int NC>
+int run_tf32_tma(nq_ctx_t ctx, const float* X, int64_t ldr, int64_t P, int64_t Ns, int64_t Ns_total, bool out_complex, float* dS,
+                 bool* used) {
+    *used = false;
+    static PFN_cuTensorMapEncodeTiled encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        cudaGetLastError();
+        return (PFN_cuTensorMapEncodeTiled)fn;
+    }();
+    if (!encode) return NQ_OK;
+    const int ntile = (int)((P + TS - 1) / TS);
+    const int64_t Ppad = (int64_t)ntile * TS, ntri = (int64_t)ntile * (ntile + 1) / 2;
+    const int64_t Nspad = (Ns + KB_T - 1) / KB_T * KB_T;
+    const int64_t rows_total = 2 * NC * Ppad;
+    if (rows_total > 0x7fffffff || Nspad > 0x7fffffff) return NQ_OK;
+    const size_t obytes = (size_t)rows_total * Nspad * sizeof(float);
+    float* ops = (float*)nq_scratch(ctx, SL_W4, obytes);
+    if (!ops) { cudaGetLastError(); return NQ_OK; }                  // not enough memory for the operand copy: staging kernel
+    {
+        dim3 g((unsigned)(Ppad / 32), (unsigned)(Nspad / 32)), b(32, 8);
+        if (g.y > 65535) return NQ_OK;
+        NQ_LAUNCH(ctx, tf32_split_kernel<NC>, g, b, 0, X, ldr, P, Ns, Ppad, Nspad, ops);
+    }
+    CUtensorMap tmap;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)Nspad, (cuuint64_t)rows_total};
+        const cuuint64_t gstr[1] = {(cuuint64_t)Nspad * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)KB_T, (cuuint32_t)TS};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ops, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return nq_fail(ctx, NQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+    const int64_t nchunk = Nspad / KB_T;
+    int nsplit = 1;
+    {
+        double best = 1e30;
+        const double slots = (double)ctx->num_sms;
+        for (int ns = 1; ns <= 64; ns++) {
+            if (ns > 1 && nchunk / ns < 4 * WINS) break;
+            double waves = (double)ntri * ns / slots;
+            double cost = std::ceil(waves) / waves + 0.004 * ns;
+            if (waves >= 1.0 || ns == 1) { if (cost < best) { best = cost; nsplit = ns; } }
+        }
+    }
+    const size_t plane = (size_t)Ppad * Ppad * sizeof(float);
+    while (nsplit > 1 && plane * nsplit * (out_complex ? 2 : 1) > ((size_t)3 << 30)) nsplit--;
+    float* Wre = (float*)nq_scratch(ctx, SL_W0, plane * nsplit);
+    float* Wim = out_complex ? (float*)nq_scratch(ctx, SL_W1, plane * nsplit) : nullptr;
+    unsigned* flags = (unsigned*)nq_scratch(ctx, SL_W3, (size_t)ntile * sizeof(unsigned) + 16);
+    if (!Wre || (out_complex && !Wim) || !flags) return NQ_ERR_ALLOC;
+    if (NC == 2) {
+        if (ctx->hint_P == P && (int)ctx->hint_tile_flags.size() == ntile) {
+            NQ_CUDA(ctx, cudaMemcpyAsync(flags, ctx->hint_tile_flags.data(), (size_t)ntile * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            NQ_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)ntile * sizeof(unsigned), ctx->stream));
+            dim3 g((unsigned)((P * NC + 255) / 256), (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, Ns / 64)));
+            NQ_LAUNCH(ctx, (tile_activity32_kernel<float, NC>), g, 256, 0, X, ldr, P, Ns, flags);
+        }
+    }
+    const size_t smem = (size_t)NSTG * 4 * OPB + 1024 + 256;
+    auto kern = syrk_tf32_tma_kernel<NC>;
+    NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)ntri, (unsigned)nsplit);
+    NQ_LAUNCH(ctx, kern, grid, 256, smem, tmap, Ppad, Nspad, ntile, nsplit, 0, (const unsigned*)flags, Wre);
+    if (out_complex) NQ_LAUNCH(ctx, kern, grid, 256, smem, tmap, Ppad, Nspad, ntile, nsplit, 1, (const unsigned*)flags, Wim);
+    dim3 fg((unsigned)((P + 127) / 128), (unsigned)P);
+    NQ_LAUNCH(ctx, syrk32_finalize_kernel<float>, fg, 128, 0, (const float*)Wre, (const float*)Wim, nsplit, Ppad, P,
+              1.0 / (double)Ns_total, (int)out_complex, dS);
+    *used = true;
+    return NQ_OK;
+}
+
 }  // namespace
 
 // FP32-mode S assembly (O of dtype F32 or C64); S is written as float (real) or interleaved complex float.
 int nq_syrk_tf32_device(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total, bool o_complex,
                         bool out_complex, void* dS) {
+    // default: the TMA-fed pipeline (operands pre-split into K-major planes); NQ_SR_TF32=stage forces the staging kernel,
+    // which is also the fallback when the operand copy (2 x the size of O) cannot be allocated
+    static const int want_tma = [] { const char* e = getenv("NQ_SR_TF32"); return e ? (!strcmp(e, "stage") ? 0 : 1) : 1; }();
+    if (want_tma && P <= 65535) {
+        bool used = false;
+        int st = o_complex ? run_tf32_tma<2>(ctx, (const float*)Oc, ldO * 2, P, Ns, Ns_total, out_complex, (float*)dS, &used)
+                           : run_tf32_tma<1>(ctx, (const float*)Oc, ldO, P, Ns, Ns_total, false, (float*)dS, &used);
+        if (st != NQ_OK || used) return st;
+    }
     if (o_complex) return run_tf32<2>(ctx, (const float*)Oc, ldO * 2, P, Ns, Ns_total, out_complex, (float*)dS);
     return run_tf32<1>(ctx, (const float*)Oc, ldO, P, Ns, Ns_total, false, (float*)dS);
 }
