@@ -71,3 +71,6 @@ int nq_stage_pack(nq_machine_t m, NqStage& st, const void* srow, const void* sco
 // nq_syrk_tf32.cu: FP32-mode S assembly on tcgen05 (3xTF32); S written as float / interleaved complex float
 int nq_syrk_tf32_device(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, int64_t Ns_total, bool o_complex,
                         bool out_complex, void* dS);
+// nq_syrk_ozaki.cu: FP64 S assembly (real part) on the integer tensor cores; *used = false -> run the DMMA kernel instead
+int nq_syrk_ozaki_device(nq_ctx_t ctx, const double* Xr, int64_t ldr, int64_t P, int64_t Ns, int NC, int ntile, int nsplit, double* W,
+                         bool* used);

@@ -2049,16 +2049,22 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
     double* Wre = (double*)nq_scratch(ctx, SL_W0, plane * nsplit);
     double* Wim = out_complex ? (double*)nq_scratch(ctx, SL_W1, plane * nsplit) : nullptr;
     if (!Wre || (out_complex && !Wim)) return NQ_ERR_ALLOC;
+    // FP64: the real part runs on the integer tensor cores (Ozaki scheme, nq_syrk_ozaki.cu) from 1024 samples on; NQ_SR_FP64=dmma
+    // forces the DMMA kernel (which is also the fallback when the digit planes cannot be allocated)
+    static const int want_ozaki = [] { const char* e = getenv("NQ_SR_FP64"); return e ? (!strcmp(e, "dmma") ? 0 : 1) : 1; }();
+    bool oz = false;
+    if (want_ozaki && nq_dtype_is_double(dtype) && Ns >= 1024)
+        NQ_CHECK(nq_syrk_ozaki_device(ctx, (const double*)Oc, ldr, P, Ns, ocx ? 2 : 1, ntile, nsplit, Wre, &oz));
     if (ocx) {
         if (nq_dtype_is_double(dtype)) {
-            NQ_CHECK((launch_syrk<double, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
+            if (!oz) NQ_CHECK((launch_syrk<double, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
             if (out_complex) NQ_CHECK((launch_syrk<double, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 1, Wim)));
         } else {
             NQ_CHECK((launch_syrk<float, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
             if (out_complex) NQ_CHECK((launch_syrk<float, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 1, Wim)));
         }
     } else {
-        if (nq_dtype_is_double(dtype)) NQ_CHECK((launch_syrk<double, 1>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
+        if (nq_dtype_is_double(dtype)) { if (!oz) NQ_CHECK((launch_syrk<double, 1>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre))); }
         else NQ_CHECK((launch_syrk<float, 1>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
     }
     dim3 grid((unsigned)((P + 127) / 128), (unsigned)std::min<int64_t>(P, 65535));
