@@ -2054,11 +2054,11 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
     static const int want_ozaki = [] { const char* e = getenv("NQ_SR_FP64"); return e ? (!strcmp(e, "dmma") ? 0 : 1) : 1; }();
     bool oz = false;
     if (want_ozaki && nq_dtype_is_double(dtype) && Ns >= 1024)
-        NQ_CHECK(nq_syrk_ozaki_device(ctx, (const double*)Oc, ldr, P, Ns, ocx ? 2 : 1, ntile, nsplit, Wre, &oz));
+        NQ_CHECK(nq_syrk_ozaki_device(ctx, (const double*)Oc, ldr, P, Ns, ocx ? 2 : 1, ntile, nsplit, Wre, out_complex ? Wim : nullptr, &oz));
     if (ocx) {
         if (nq_dtype_is_double(dtype)) {
             if (!oz) NQ_CHECK((launch_syrk<double, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
-            if (out_complex) NQ_CHECK((launch_syrk<double, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 1, Wim)));
+            if (out_complex && !oz) NQ_CHECK((launch_syrk<double, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 1, Wim)));
         } else {
             NQ_CHECK((launch_syrk<float, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
             if (out_complex) NQ_CHECK((launch_syrk<float, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 1, Wim)));

@@ -16,7 +16,8 @@
 //               + 7 B slices = 84 KB), warp 1 = MMA issuer (per stage 2 k-steps x 34 products, M = 128, N = 64, K = 32, one
 //               TMEM accumulator of 64 columns per diagonal d = p + q: 8 x 64 = all 512 columns), warps 4-7 = epilogue (int32 ->
 //               double, 2^(-7d) and the row / column scales, split-K partials in double)
-// The (re, im) planes of complex rows enter as extra K items and share one exponent per parameter row.
+// The (re, im) planes of complex rows enter as extra K items and share one exponent per parameter row; the imaginary part of a
+// complex S is a second launch on the planes (re, im) and (-im, re) (the pre-pass also writes the negated imaginary digits).
 #include "nq_internal.cuh"
 #include <algorithm>
 #include <cuda.h>
@@ -113,7 +114,7 @@ __global__ void oz_activity_kernel(const double* __restrict__ Xr, int64_t ldr, i
 template <int NC>
 __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, int64_t Ppad,
                                                        int64_t Nspad, const unsigned long long* __restrict__ mx,
-                                                       signed char* __restrict__ out, int* __restrict__ ex) {
+                                                       signed char* __restrict__ out, int* __restrict__ ex, int neg_plane) {
     extern __shared__ signed char tile[];                 // [NSL][32 NC][128 + 4]
     constexpr int ROWS = 32 * NC, LD = 128 + 4;
     const int tid = threadIdx.x;
@@ -158,12 +159,16 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
     __syncthreads();
     // write: one (slice, component, row) line of 128 bytes per warp instruction
     const int warp = tid >> 5, lane = tid & 31;
+    // planes per slice: the NC components, then (neg_plane) the NEGATED imaginary digits -- the imaginary part of S needs
+    // A_re B_im^T - A_im B_re^T and the integer MMA has no negate flag
     const size_t plane = (size_t)Ppad * Nspad;
+    const int NP = NC + neg_plane;
     for (int line = warp; line < NSL * ROWS; line += 8) {
         const int p = line / ROWS, r2 = line % ROWS, c = r2 % NC, kk = r2 / NC;
         const int word = *reinterpret_cast<const int*>(&tile[(p * ROWS + r2) * LD + 4 * lane]);
-        if (s0 + 4 * lane < Nspad)
-            *reinterpret_cast<int*>(out + ((size_t)(p * NC + c)) * plane + (size_t)(k0 + kk) * Nspad + s0 + 4 * lane) = word;
+        const size_t at = (size_t)(k0 + kk) * Nspad + s0 + 4 * lane;
+        *reinterpret_cast<int*>(out + ((size_t)(p * NP + c)) * plane + at) = word;
+        if (neg_plane && c == 1) *reinterpret_cast<int*>(out + ((size_t)(p * NP + 2)) * plane + at) = (int)__vneg4((unsigned)word);
     }
 }
 
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
 template <int NC>
 __global__ void __launch_bounds__(256, 1)
 syrk_ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int64_t Ppad, int64_t Nspad,
-                  int ntile, int nsplit, const unsigned* __restrict__ tflags, const int* __restrict__ ex,
+                  int ntile, int nsplit, int mode, int NP, const unsigned* __restrict__ tflags, const int* __restrict__ ex,
                   double* __restrict__ Wk /* [nsplit][Ppad*Ppad] col-major */) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
@@ -194,9 +199,13 @@ syrk_ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int64_t c_begin = split * cper, c_end = std::min<int64_t>(nchunk_tot, c_begin + cper);
 
     const unsigned fa = NC == 2 ? tflags[ti] : 1u, fb = NC == 2 ? tflags[tj >> 1] : 1u;
+    // mode 0 (real part): sum_c A_c B_c^T.  mode 1 (imaginary part): A_re B_im^T + (-A_im) B_re^T, planes (0, 1) and (2, 0)
     int comps[2], ncomp = 0;
-    for (int c = 0; c < NC; c++) if (((fa >> c) & 1u) && ((fb >> c) & 1u)) comps[ncomp++] = c;
-    const bool same = (tj >> 1) == ti;                  // the B rows are a half of the A rows: no B boxes
+    for (int c = 0; c < NC; c++) {
+        const unsigned bc = mode == 0 ? c : 1 - c;
+        if (((fa >> c) & 1u) && ((fb >> bc) & 1u)) comps[ncomp++] = c;
+    }
+    const bool same = mode == 0 && (tj >> 1) == ti;     // the B rows are a half of the A rows: no B boxes
     const int64_t nit = (c_end > c_begin ? c_end - c_begin : 0) * ncomp;
     const int64_t nwin = (nit + WIN_ITEMS - 1) / WIN_ITEMS;
 
@@ -220,16 +229,17 @@ syrk_ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const int s = (int)(it % NSTG);
             mbar_wait(&empty[s], (uint32_t)(((it / NSTG) & 1) ^ 1));
             const int comp = comps[it % ncomp];
+            const int pa = mode == 0 ? comp : (comp == 0 ? 0 : 2), pb = mode == 0 ? comp : (comp == 0 ? 1 : 0);
             const int32_t k0 = (int32_t)((c_begin + it / ncomp) * KBYTES);
             const uint32_t st = smem_u32(base + (size_t)s * STAGE);
             mbar_expect_tx(&full[s], (uint32_t)(same ? NSL * ABOX : STAGE));
 #pragma unroll
             for (int p = 0; p < NSL; p++)
-                tma_load_2d(st + p * ABOX, &mapA, k0, (int32_t)((int64_t)(p * NC + comp) * Ppad + (int64_t)ti * TM), &full[s]);
+                tma_load_2d(st + p * ABOX, &mapA, k0, (int32_t)((int64_t)(p * NP + pa) * Ppad + (int64_t)ti * TM), &full[s]);
             if (!same) {
 #pragma unroll
                 for (int p = 0; p < NSL; p++)
-                    tma_load_2d(st + NSL * ABOX + p * BBOX, &mapB, k0, (int32_t)((int64_t)(p * NC + comp) * Ppad + (int64_t)tj * TN), &full[s]);
+                    tma_load_2d(st + NSL * ABOX + p * BBOX, &mapB, k0, (int32_t)((int64_t)(p * NP + pb) * Ppad + (int64_t)tj * TN), &full[s]);
             }
         }
     } else if (warp == 1 && lane == 0) {
@@ -312,13 +322,14 @@ PFN_cuTensorMapEncodeTiled get_encode() {
 }
 
 template <int NC>
-int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns, int ntile, int nsplit, double* W, bool* used) {
+int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns, int ntile, int nsplit, double* W, double* Wim, bool* used) {
     *used = false;
     PFN_cuTensorMapEncodeTiled encode = get_encode();
     if (!encode) return NQ_OK;
     const int64_t Ppad = (int64_t)ntile * TM;
     const int64_t Nspad = (Ns + 127) / 128 * 128;
-    const int64_t rows_total = (int64_t)NSL * NC * Ppad;
+    const int neg_plane = (NC == 2 && Wim) ? 1 : 0, NP = NC + neg_plane;
+    const int64_t rows_total = (int64_t)NSL * NP * Ppad;
     if (rows_total > 0x7fffffff || Nspad > 0x7fffffff || Nspad / 128 > 65535) return NQ_OK;
     const size_t obytes = (size_t)rows_total * Nspad;
     signed char* ops = (signed char*)nq_scratch(ctx, SL_W4, obytes);
@@ -346,7 +357,7 @@ int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns,
         const size_t smem = (size_t)NSL * 32 * NC * (128 + 4);
         auto ks = oz_split_kernel<NC>;
         NQ_CUDA(ctx, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NQ_LAUNCH(ctx, ks, g, 256, smem, X, ldr, P, Ns, Ppad, Nspad, (const unsigned long long*)mx, ops, ex);
+        NQ_LAUNCH(ctx, ks, g, 256, smem, X, ldr, P, Ns, Ppad, Nspad, (const unsigned long long*)mx, ops, ex, neg_plane);
     }
     CUtensorMap mapA, mapB;
     {
@@ -364,18 +375,20 @@ int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns,
     auto kern = syrk_ozaki_kernel<NC>;
     NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((int64_t)ntile * (ntile + 1)), (unsigned)nsplit);
-    NQ_LAUNCH(ctx, kern, grid, 256, smem, mapA, mapB, Ppad, Nspad, ntile, nsplit, (const unsigned*)flags, (const int*)ex, W);
+    NQ_LAUNCH(ctx, kern, grid, 256, smem, mapA, mapB, Ppad, Nspad, ntile, nsplit, 0, NP, (const unsigned*)flags, (const int*)ex, W);
+    if (neg_plane) NQ_LAUNCH(ctx, kern, grid, 256, smem, mapA, mapB, Ppad, Nspad, ntile, nsplit, 1, NP, (const unsigned*)flags, (const int*)ex, Wim);
     *used = true;
     return NQ_OK;
 }
 
 }  // namespace
 
-// Re(O O^H) (mode 0) split-K partials W [nsplit][Ppad^2] (doubles, column-major, lower 128-tiles and the full diagonal
-// tiles) from the real rows Xr [(k NC + c) + ldr s].  *used = false when the path is not available (no driver entry
-// point, not enough memory for the digit planes): the caller runs the DMMA kernel instead.
+// Split-K partials of conj(O O^H): the real part W and, for complex S (Wim != NULL, NC = 2), the imaginary part Wim --
+// [nsplit][Ppad^2] doubles, column-major, lower 128-tiles and the full diagonal tiles -- from the real rows
+// Xr [(k NC + c) + ldr s].  *used = false when the path is not available (no driver entry point, not enough memory for the
+// digit planes): the caller runs the DMMA kernel instead.
 int nq_syrk_ozaki_device(nq_ctx_t ctx, const double* Xr, int64_t ldr, int64_t P, int64_t Ns, int NC, int ntile, int nsplit, double* W,
-                         bool* used) {
-    if (NC == 2) return run_ozaki<2>(ctx, Xr, ldr, P, Ns, ntile, nsplit, W, used);
-    return run_ozaki<1>(ctx, Xr, ldr, P, Ns, ntile, nsplit, W, used);
+                         double* Wim, bool* used) {
+    if (NC == 2) return run_ozaki<2>(ctx, Xr, ldr, P, Ns, ntile, nsplit, W, Wim, used);
+    return run_ozaki<1>(ctx, Xr, ldr, P, Ns, ntile, nsplit, W, nullptr, used);
 }
