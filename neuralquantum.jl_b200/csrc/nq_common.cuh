@@ -34,6 +34,12 @@ struct nq_ctx_s {
     // of O may be non-zero (bit 0 = re, bit 1 = im); replaces the scan of O by tile_activity_kernel
     std::vector<unsigned> hint_tile_flags;
     int64_t hint_P = 0;
+    // row maxima of the matrix the last centring pass wrote (one-shot, consumed by the next nq_sr_setup on the same matrix):
+    // the Ozaki S assembly scales every row by its exponent and would otherwise read O once more to find it
+    unsigned long long* rowmax = nullptr;      // device [rowmax_cap] bit patterns of max |x| per parameter row
+    int64_t rowmax_cap = 0;
+    const void* rowmax_ptr = nullptr;
+    int64_t rowmax_P = 0, rowmax_Ns = 0, rowmax_ld = 0;
 };
 
 int nq_fail(nq_ctx_t ctx, int code, const char* fmt, ...);

@@ -115,22 +115,43 @@ int colsum_dispatch(nq_ctx_t ctx, nq_dtype dtype, const void* X, int64_t ld, int
     }
 }
 
+// X <- X - avg; mx (optional): running maximum of |centred value| per parameter row (both components), see nq_ctx_s::rowmax
 template <typename E>
-__global__ void subtract_avg_kernel(E* __restrict__ X, int64_t ld, int64_t P, int64_t Ns, const cxd* __restrict__ avg) {
+__global__ void subtract_avg_kernel(E* __restrict__ X, int64_t ld, int64_t P, int64_t Ns, const cxd* __restrict__ avg,
+                                    unsigned long long* __restrict__ mx) {
     typedef typename elem_traits<E>::real T;
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= P) return;
     cxd a = avg[k];
+    double m = 0.0;
     for (int64_t s = blockIdx.y; s < Ns; s += gridDim.y) {
         E x = X[k + ld * s];
         if (elem_traits<E>::is_complex) {
             cx<T>* px = (cx<T>*)&X[k + ld * s];
-            *px = cx<T>((T)((double)real_part(x) - a.re), (T)((double)imag_part(x) - a.im));
+            const cx<T> y((T)((double)real_part(x) - a.re), (T)((double)imag_part(x) - a.im));
+            *px = y;
+            m = fmax(m, fmax(fabs((double)y.re), fabs((double)y.im)));
         } else {
             T* px = (T*)&X[k + ld * s];
-            *px = (T)((double)real_part(x) - a.re);
+            const T y = (T)((double)real_part(x) - a.re);
+            *px = y;
+            m = fmax(m, fabs((double)y));
         }
     }
+    if (mx) atomicMax(&mx[k], (unsigned long long)__double_as_longlong(m));
+}
+
+// (re)arm the one-shot row-maximum record of the context for the matrix X about to be centred; returns the device buffer
+static unsigned long long* rowmax_arm(nq_ctx_t ctx, const void* X, int64_t ld, int64_t P, int64_t Ns) {
+    ctx->rowmax_ptr = nullptr;
+    if (ctx->rowmax_cap < P) {
+        if (ctx->rowmax) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->rowmax); ctx->rowmax = nullptr; ctx->rowmax_cap = 0; }
+        if (cudaMalloc((void**)&ctx->rowmax, (size_t)(P + P / 4 + 64) * 8) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        ctx->rowmax_cap = P + P / 4 + 64;
+    }
+    if (cudaMemsetAsync(ctx->rowmax, 0, (size_t)P * 8, ctx->stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ctx->rowmax_ptr = X; ctx->rowmax_P = P; ctx->rowmax_Ns = Ns; ctx->rowmax_ld = ld;
+    return ctx->rowmax;
 }
 
 // convert a cxd vector to dtype (real dtypes take the real part)
@@ -1914,11 +1935,12 @@ extern "C" int nq_center(nq_ctx_t ctx, void* O_user, int64_t ldO, int64_t P, int
         a = tmp;
     }
     dim3 grid((unsigned)((P + 127) / 128), (unsigned)std::min<int64_t>(Ns, 4096));
+    unsigned long long* mx = (nq_dtype_is_double(dtype) && !o_on_host) ? rowmax_arm(ctx, O, ldO, P, Ns) : nullptr;
     switch (dtype) {
-        case NQ_F32: NQ_LAUNCH(ctx, subtract_avg_kernel<float>, grid, 128, 0, (float*)O, ldO, P, Ns, (const cxd*)a); break;
-        case NQ_F64: NQ_LAUNCH(ctx, subtract_avg_kernel<double>, grid, 128, 0, (double*)O, ldO, P, Ns, (const cxd*)a); break;
-        case NQ_C64: NQ_LAUNCH(ctx, subtract_avg_kernel<cxf>, grid, 128, 0, (cxf*)O, ldO, P, Ns, (const cxd*)a); break;
-        default: NQ_LAUNCH(ctx, subtract_avg_kernel<cxd>, grid, 128, 0, (cxd*)O, ldO, P, Ns, (const cxd*)a); break;
+        case NQ_F32: NQ_LAUNCH(ctx, subtract_avg_kernel<float>, grid, 128, 0, (float*)O, ldO, P, Ns, (const cxd*)a, mx); break;
+        case NQ_F64: NQ_LAUNCH(ctx, subtract_avg_kernel<double>, grid, 128, 0, (double*)O, ldO, P, Ns, (const cxd*)a, mx); break;
+        case NQ_C64: NQ_LAUNCH(ctx, subtract_avg_kernel<cxf>, grid, 128, 0, (cxf*)O, ldO, P, Ns, (const cxd*)a, mx); break;
+        default: NQ_LAUNCH(ctx, subtract_avg_kernel<cxd>, grid, 128, 0, (cxd*)O, ldO, P, Ns, (const cxd*)a, mx); break;
     }
     NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)a, davg, P, (int)dtype, 0);
     if (o_on_host) {      // centred O goes back to the caller's array (the reference centres in place)
@@ -2053,8 +2075,13 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
     // forces the DMMA kernel (which is also the fallback when the digit planes cannot be allocated)
     static const int want_ozaki = [] { const char* e = getenv("NQ_SR_FP64"); return e ? (!strcmp(e, "dmma") ? 0 : 1) : 1; }();
     bool oz = false;
+    // row maxima left by the centring pass of this very matrix (one-shot): the Ozaki pre-pass skips its own read of O
+    const unsigned long long* known_max = (ctx->rowmax_ptr == Oc && ctx->rowmax_P == P && ctx->rowmax_Ns == Ns && ctx->rowmax_ld == ldO)
+                                              ? ctx->rowmax : nullptr;
+    ctx->rowmax_ptr = nullptr;
     if (want_ozaki && nq_dtype_is_double(dtype) && Ns >= 1024)
-        NQ_CHECK(nq_syrk_ozaki_device(ctx, (const double*)Oc, ldr, P, Ns, ocx ? 2 : 1, ntile, nsplit, Wre, out_complex ? Wim : nullptr, &oz));
+        NQ_CHECK(nq_syrk_ozaki_device(ctx, (const double*)Oc, ldr, P, Ns, ocx ? 2 : 1, ntile, nsplit, Wre, out_complex ? Wim : nullptr,
+                                      known_max, &oz));
     if (ocx) {
         if (nq_dtype_is_double(dtype)) {
             if (!oz) NQ_CHECK((launch_syrk<double, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));
@@ -2367,11 +2394,12 @@ extern "C" int nq_sr_accumulate(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, i
     {   // O_c <- O_c - c in place (the chunk buffer is the caller's scratch)
         dim3 grid((unsigned)((P + 127) / 128), (unsigned)std::min<int64_t>(Nc, 4096));
         const cxd* c = (const cxd*)state + P;
+        unsigned long long* mx = nq_dtype_is_double(dtype) ? rowmax_arm(ctx, O, ldO, P, Nc) : nullptr;
         switch (dtype) {
-            case NQ_F32: NQ_LAUNCH(ctx, subtract_avg_kernel<float>, grid, 128, 0, (float*)O, ldO, P, Nc, c); break;
-            case NQ_F64: NQ_LAUNCH(ctx, subtract_avg_kernel<double>, grid, 128, 0, (double*)O, ldO, P, Nc, c); break;
-            case NQ_C64: NQ_LAUNCH(ctx, subtract_avg_kernel<cxf>, grid, 128, 0, (cxf*)O, ldO, P, Nc, c); break;
-            default: NQ_LAUNCH(ctx, subtract_avg_kernel<cxd>, grid, 128, 0, (cxd*)O, ldO, P, Nc, c); break;
+            case NQ_F32: NQ_LAUNCH(ctx, subtract_avg_kernel<float>, grid, 128, 0, (float*)O, ldO, P, Nc, c, mx); break;
+            case NQ_F64: NQ_LAUNCH(ctx, subtract_avg_kernel<double>, grid, 128, 0, (double*)O, ldO, P, Nc, c, mx); break;
+            case NQ_C64: NQ_LAUNCH(ctx, subtract_avg_kernel<cxf>, grid, 128, 0, (cxf*)O, ldO, P, Nc, c, mx); break;
+            default: NQ_LAUNCH(ctx, subtract_avg_kernel<cxd>, grid, 128, 0, (cxd*)O, ldO, P, Nc, c, mx); break;
         }
     }
     // chunk Gram matrix with the global normalisation into a scratch S (the first chunk goes straight to Sacc)

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
     } else if (rr % NC == 0 && blockIdx.y == 0 && sl0 == 0 && k < Ppad) {
         ex[k] = 0;
     }
-    const double sc = scalbn(1.0, -e);
+    const double sc49 = scalbn(1.0, 7 * NSL - e);          // x 2^-e in (-1/2, 1/2), times 2^49
     for (int i0 = sl0; i0 < 128; i0 += 8 * SLN) {           // 8 independent loads in flight per thread
         double yv[8];
 #pragma unroll
@@ -143,17 +143,16 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
         for (int u = 0; u < 8; u++) {
             const int i = i0 + u * SLN;
             if (i >= 128) continue;
-            // digit = rint(128 y) through the 1.5 * 2^52 trick: the low word of (t + magic) holds the integer, (t + magic) -
-            // magic is rint(t) exactly -- three FP64 adds instead of a round and a double -> int conversion (4x slower pipe)
-            const double magic = 6755399441055744.0;
-            double y = yv[u] * sc;
+            // y 2^49 as a 64-bit integer (|y| < 1/2: 48 bits), then 7 balanced base-128 digits, least significant first, with
+            // integer shifts and adds (the FP64 round / subtract chain of the first version cost twice the issue slots)
+            long long v = __double2ll_rn(yv[u] * sc49);
 #pragma unroll
-            for (int p = 0; p < NSL; p++) {
-                const double t = y * 128.0;
-                const double m = t + magic;
-                y = t - (m - magic);
-                tile[(p * ROWS + rr) * LD + i] = (signed char)__double2loint(m);
+            for (int p = NSL - 1; p >= 1; p--) {
+                const int q = (int)((v + 64) & 127) - 64;
+                v = (v - q) >> 7;
+                tile[(p * ROWS + rr) * LD + i] = (signed char)q;
             }
+            tile[rr * LD + i] = (signed char)v;              // top digit, |v| <= 64
         }
     }
     __syncthreads();
@@ -310,6 +309,195 @@ syrk_ozaki_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
 }
 
+
+// =====================================================================================================================
+// v2: 128 x 128 tiles in TWO passes over K.  The 128 x 64 kernel above reads 6 KB of operands from shared memory per 34-cycle
+// MMA (A 128 x 32 B + B 64 x 32 B): 180 B/clk against the 128 B/clk the SM delivers -- its tensor pipe saturates at ~52 %.
+// With N = 128 an MMA reads 8 KB per 68 cycles.  Four accumulators of 128 columns fill the TMEM, so the diagonals are done
+// in two groups: pass A = d 2..5 (10 products, slices 1..4 of both operands: 8 boxes = 64 KB per stage, 3 stages), pass B =
+// d 6..9 (24 products, all 7 slices: 14 boxes = 112 KB per stage, 2 stages).  The operand traffic from L2 is the same as for
+// two 128 x 64 tiles (176 vs 168 KB per 64 samples).  The epilogue adds each pass into the FP64 split-K partial in global
+// memory, 32 columns at a time (a whole 128-column row in registers would need 256 of them).
+// =====================================================================================================================
+constexpr int T2 = 128;
+constexpr int BOX2 = T2 * KBYTES;                    // 8 KB
+constexpr int STAGE_A = 8 * BOX2, NSTG_A = 3;        // slices 1..4 of A and of B
+constexpr int STAGE_B = 2 * NSL * BOX2, NSTG_B = 2;  // slices 1..7 of A and of B
+constexpr int SMEM2 = (NSTG_A * STAGE_A > NSTG_B * STAGE_B ? NSTG_A * STAGE_A : NSTG_B * STAGE_B);
+constexpr uint32_t IDESC_I8_2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T2 >> 3) << 17) | ((uint32_t)(T2 >> 4) << 24);
+__device__ __forceinline__ void mma_i8_2(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(IDESC_I8_2), "r"(accumulate) : "memory");
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256, 1)
+syrk_ozaki2_kernel(const __grid_constant__ CUtensorMap mapA, int64_t Ppad, int64_t Nspad, int ntile, int nsplit, int mode, int NP,
+                   const unsigned* __restrict__ tflags, const int* __restrict__ ex, double* __restrict__ Wk) {
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + SMEM2);
+    uint64_t* empty = full + 3;
+    uint64_t* accfull = empty + 3;
+    uint64_t* accempty = accfull + 1;
+    uint64_t* passdone = accempty + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(passdone + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    int t = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
+    while (ti * (ti + 1) / 2 > t) ti--;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int split = blockIdx.y;
+    const int64_t nchunk_tot = Nspad / KBYTES;
+    const int64_t cper = (nchunk_tot + nsplit - 1) / nsplit;
+    const int64_t c_begin = split * cper, c_end = std::min<int64_t>(nchunk_tot, c_begin + cper);
+
+    const unsigned fa = NC == 2 ? tflags[ti] : 1u, fb = NC == 2 ? tflags[tj] : 1u;
+    int comps[2], ncomp = 0;
+    for (int c = 0; c < NC; c++) {
+        const unsigned bc = mode == 0 ? c : 1 - c;
+        if (((fa >> c) & 1u) && ((fb >> bc) & 1u)) comps[ncomp++] = c;
+    }
+    const bool same = mode == 0 && ti == tj;            // B is A itself: no B boxes
+    const int64_t nit = (c_end > c_begin ? c_end - c_begin : 0) * ncomp;      // items per pass
+    const int64_t nwin = (nit + WIN_ITEMS - 1) / WIN_ITEMS;                  // windows per pass
+
+    if (tid == 0) {
+        for (int i = 0; i < 3; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(accfull, 1); mbar_init(accempty, 4); mbar_init(passdone, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---- TMA producer
+        uint32_t uses[3] = {0, 0, 0};
+        for (int pass = 0; pass < 2; pass++) {
+            const int nstg = pass == 0 ? NSTG_A : NSTG_B, nsl = pass == 0 ? 4 : NSL;
+            const uint32_t stage_bytes = pass == 0 ? STAGE_A : STAGE_B;
+            if (pass == 1) mbar_wait(passdone, 0);                    // every MMA of pass A has read its operands
+            for (int64_t it = 0; it < nit; it++) {
+                const int s = (int)(it % nstg);
+                mbar_wait(&empty[s], (uses[s] & 1u) ^ 1u);
+                uses[s]++;
+                const int comp = comps[it % ncomp];
+                const int pa = mode == 0 ? comp : (comp == 0 ? 0 : 2), pb = mode == 0 ? comp : (comp == 0 ? 1 : 0);
+                const int32_t k0 = (int32_t)((c_begin + it / ncomp) * KBYTES);
+                const uint32_t st = smem_u32(base) + (uint32_t)s * stage_bytes;
+                mbar_expect_tx(&full[s], (uint32_t)((same ? 1 : 2) * nsl * BOX2));
+                for (int p = 0; p < nsl; p++)
+                    tma_load_2d(st + p * BOX2, &mapA, k0, (int32_t)((int64_t)(p * NP + pa) * Ppad + (int64_t)ti * T2), &full[s]);
+                if (!same)
+                    for (int p = 0; p < nsl; p++)
+                        tma_load_2d(st + (nsl + p) * BOX2, &mapA, k0, (int32_t)((int64_t)(p * NP + pb) * Ppad + (int64_t)tj * T2), &full[s]);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---- MMA issuer: accumulator of diagonal d at TMEM columns 128 (d - dlo)
+        uint32_t uses[3] = {0, 0, 0};
+        int64_t wglob = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            const int nstg = pass == 0 ? NSTG_A : NSTG_B, nsl = pass == 0 ? 4 : NSL;
+            const uint32_t stage_bytes = pass == 0 ? STAGE_A : STAGE_B;
+            for (int64_t it = 0; it < nit; it++) {
+                const int s = (int)(it % nstg);
+                const bool win_first = it % WIN_ITEMS == 0;
+                if (win_first) {
+                    mbar_wait(accempty, (uint32_t)((wglob & 1) ^ 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                mbar_wait(&full[s], uses[s] & 1u);
+                uses[s]++;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = smem_u32(base) + (uint32_t)s * stage_bytes;
+                const uint32_t b0 = same ? a0 : a0 + (uint32_t)nsl * BOX2;
+                if (pass == 0) {
+#pragma unroll
+                    for (int kk = 0; kk < KBYTES / 32; kk++)
+#pragma unroll
+                        for (int d = 2; d <= 5; d++)
+#pragma unroll
+                            for (int p = 1; p < d; p++)
+                                mma_i8_2(tmem + (uint32_t)((d - 2) * T2), make_desc_sw64(a0 + (p - 1) * BOX2 + kk * 32),
+                                         make_desc_sw64(b0 + (d - p - 1) * BOX2 + kk * 32), (win_first && kk == 0 && p == 1) ? 0u : 1u);
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < KBYTES / 32; kk++)
+#pragma unroll
+                        for (int d = 6; d <= DMAX; d++)
+#pragma unroll
+                            for (int p = 1; p < d; p++) {
+                                if (p > NSL || d - p > NSL) continue;
+                                mma_i8_2(tmem + (uint32_t)((d - 6) * T2), make_desc_sw64(a0 + (p - 1) * BOX2 + kk * 32),
+                                         make_desc_sw64(b0 + (d - p - 1) * BOX2 + kk * 32),
+                                         (win_first && kk == 0 && p == (d - NSL > 1 ? d - NSL : 1)) ? 0u : 1u);
+                            }
+                }
+                umma_commit(&empty[s]);
+                if (it % WIN_ITEMS == WIN_ITEMS - 1 || it + 1 == nit) { umma_commit(accfull); wglob++; }
+            }
+            if (pass == 0) umma_commit(passdone);
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue: thread = row of the tile; every window of every pass is added into the FP64 partial, 32 columns at a time
+        double* W = Wk + (size_t)split * Ppad * Ppad;
+        const int64_t row = (int64_t)ti * T2 + (warp & 3) * 32 + lane;
+        const int64_t col0 = (int64_t)tj * T2;
+        const int er = ex[row];
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        int64_t wglob = 0;
+        bool first_write = true;
+        if (nit == 0) {
+            for (int i = 0; i < T2; i++) W[row + Ppad * (col0 + i)] = 0.0;
+        }
+        for (int pass = 0; pass < 2; pass++) {
+            const int dlo = pass == 0 ? 2 : 6;
+            for (int64_t w = 0; w < nwin; w++, wglob++) {
+                mbar_wait(accfull, (uint32_t)(wglob & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int h = 0; h < T2 / 32; h++) {
+                    double acc[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i++) acc[i] = 0.0;
+#pragma unroll
+                    for (int dd = 0; dd < 4; dd++) {
+                        const double sc = scalbn(1.0, -7 * (dlo + dd));
+                        uint32_t r[32];
+                        tmem_ld32(tmem + lane_base + (uint32_t)(dd * T2 + 32 * h), r);
+#pragma unroll
+                        for (int i = 0; i < 32; i++) acc[i] = fma((double)(int)r[i], sc, acc[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        double* dst = W + row + Ppad * (col0 + 32 * h + i);
+                        const double v = scalbn(acc[i], er + ex[col0 + 32 * h + i]);
+                        *dst = first_write ? v : *dst + v;
+                    }
+                }
+                first_write = false;
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(accempty);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}
+
 PFN_cuTensorMapEncodeTiled get_encode() {
     static PFN_cuTensorMapEncodeTiled encode = [] {
         void* fn = nullptr;
@@ -322,7 +510,8 @@ PFN_cuTensorMapEncodeTiled get_encode() {
 }
 
 template <int NC>
-int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns, int ntile, int nsplit, double* W, double* Wim, bool* used) {
+int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns, int ntile, int nsplit, double* W, double* Wim,
+              const unsigned long long* known_rowmax, bool* used) {
     *used = false;
     PFN_cuTensorMapEncodeTiled encode = get_encode();
     if (!encode) return NQ_OK;
@@ -339,10 +528,14 @@ int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns,
     int* ex = (int*)(mx + Ppad);
     unsigned* flags = (unsigned*)nq_scratch(ctx, SL_W3, (size_t)ntile * sizeof(unsigned) + 16);
     if (!flags) return NQ_ERR_ALLOC;
-    NQ_CUDA(ctx, cudaMemsetAsync(mx, 0, (size_t)Ppad * 8, ctx->stream));
     {
         dim3 g((unsigned)((P * NC + 255) / 256), (unsigned)std::max<int64_t>(1, std::min<int64_t>(64, Ns / 64)));
-        NQ_LAUNCH(ctx, oz_rowmax_kernel<NC>, g, 256, 0, X, ldr, P, Ns, mx);
+        if (known_rowmax) {
+            NQ_CUDA(ctx, cudaMemcpyAsync(mx, known_rowmax, (size_t)P * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            NQ_CUDA(ctx, cudaMemsetAsync(mx, 0, (size_t)Ppad * 8, ctx->stream));
+            NQ_LAUNCH(ctx, oz_rowmax_kernel<NC>, g, 256, 0, X, ldr, P, Ns, mx);
+        }
         if (NC == 2) {
             if (ctx->hint_P == P && (int)ctx->hint_tile_flags.size() == ntile) {
                 NQ_CUDA(ctx, cudaMemcpyAsync(flags, ctx->hint_tile_flags.data(), (size_t)ntile * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
@@ -371,6 +564,25 @@ int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns,
                              (KBYTES == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return nq_fail(ctx, NQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
     }
+    static const int want_v1 = [] { const char* e = getenv("NQ_OZAKI"); return (e && !strcmp(e, "v1")) ? 1 : 0; }();
+    if (!want_v1) {
+        CUtensorMap map2;
+        const cuuint64_t gdim[2] = {(cuuint64_t)Nspad, (cuuint64_t)rows_total};
+        const cuuint64_t gstr[1] = {(cuuint64_t)Nspad};
+        const cuuint32_t box2[2] = {(cuuint32_t)KBYTES, (cuuint32_t)T2};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&map2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ops, gdim, gstr, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return nq_fail(ctx, NQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+        const size_t smem2 = (size_t)SMEM2 + 1024 + 256;
+        auto k2 = syrk_ozaki2_kernel<NC>;
+        NQ_CUDA(ctx, cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        dim3 grid2((unsigned)((int64_t)ntile * (ntile + 1) / 2), (unsigned)nsplit);
+        NQ_LAUNCH(ctx, k2, grid2, 256, smem2, map2, Ppad, Nspad, ntile, nsplit, 0, NP, (const unsigned*)flags, (const int*)ex, W);
+        if (neg_plane) NQ_LAUNCH(ctx, k2, grid2, 256, smem2, map2, Ppad, Nspad, ntile, nsplit, 1, NP, (const unsigned*)flags, (const int*)ex, Wim);
+        *used = true;
+        return NQ_OK;
+    }
     const size_t smem = (size_t)NSTG * STAGE + 1024 + 256;
     auto kern = syrk_ozaki_kernel<NC>;
     NQ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -388,7 +600,7 @@ int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns,
 // Xr [(k NC + c) + ldr s].  *used = false when the path is not available (no driver entry point, not enough memory for the
 // digit planes): the caller runs the DMMA kernel instead.
 int nq_syrk_ozaki_device(nq_ctx_t ctx, const double* Xr, int64_t ldr, int64_t P, int64_t Ns, int NC, int ntile, int nsplit, double* W,
-                         double* Wim, bool* used) {
-    if (NC == 2) return run_ozaki<2>(ctx, Xr, ldr, P, Ns, ntile, nsplit, W, Wim, used);
-    return run_ozaki<1>(ctx, Xr, ldr, P, Ns, ntile, nsplit, W, nullptr, used);
+                         double* Wim, const unsigned long long* known_rowmax, bool* used) {
+    if (NC == 2) return run_ozaki<2>(ctx, Xr, ldr, P, Ns, ntile, nsplit, W, Wim, known_rowmax, used);
+    return run_ozaki<1>(ctx, Xr, ldr, P, Ns, ntile, nsplit, W, nullptr, known_rowmax, used);
 }
