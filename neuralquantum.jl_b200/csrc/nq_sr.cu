@@ -2079,9 +2079,21 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
     const unsigned long long* known_max = (ctx->rowmax_ptr == Oc && ctx->rowmax_P == P && ctx->rowmax_Ns == Ns && ctx->rowmax_ld == ldO)
                                               ? ctx->rowmax : nullptr;
     ctx->rowmax_ptr = nullptr;
-    if (want_ozaki && nq_dtype_is_double(dtype) && Ns >= 1024)
-        NQ_CHECK(nq_syrk_ozaki_device(ctx, (const double*)Oc, ldr, P, Ns, ocx ? 2 : 1, ntile, nsplit, Wre, out_complex ? Wim : nullptr,
+    if (want_ozaki && nq_dtype_is_double(dtype) && Ns >= 1024) {
+        // its own split of K: every CTA drains its accumulators into the FP64 partial once per pass, so a split should cover
+        // >= 2048 samples (the DMMA split above goes down to 128, which at 8 192 samples per GPU made the Ozaki path slower)
+        int ns_oz = 1;
+        double best = 1e30;
+        for (int ns = 1; ns <= nsplit && ns <= 32; ns++) {
+            if (ns > 1 && Ns / ns < 2048) break;
+            const double waves = (double)ntri * ns / ctx->num_sms;
+            const double cost = std::ceil(waves) / waves + 0.01 * ns;
+            if ((waves >= 1.0 || ns == 1) && cost < best) { best = cost; ns_oz = ns; }
+        }
+        NQ_CHECK(nq_syrk_ozaki_device(ctx, (const double*)Oc, ldr, P, Ns, ocx ? 2 : 1, ntile, ns_oz, Wre, out_complex ? Wim : nullptr,
                                       known_max, &oz));
+        if (oz) nsplit = ns_oz;
+    }
     if (ocx) {
         if (nq_dtype_is_double(dtype)) {
             if (!oz) NQ_CHECK((launch_syrk<double, 2>(ctx, Oc, ldr, P, Ns, ntile, nsplit, 0, Wre)));

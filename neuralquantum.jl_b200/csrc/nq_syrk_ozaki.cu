@@ -132,27 +132,39 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
         ex[k] = 0;
     }
     const double sc49 = scalbn(1.0, 7 * NSL - e);          // x 2^-e in (-1/2, 1/2), times 2^49
-    for (int i0 = sl0; i0 < 128; i0 += 8 * SLN) {           // 8 independent loads in flight per thread
-        double yv[8];
+    // a task = 4 consecutive samples of one row: four loads (each coalesced over the 32 rows of the warp), 4 x 7 digits, packed
+    // into one 32-bit word per slice (byte stores cost four times the shared-memory instructions)
+    for (int j0 = sl0; j0 < 32; j0 += 2 * SLN) {            // two tasks (8 loads) in flight per thread
+        double yv[2][4];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int64_t smp = s0 + i0 + u * SLN;
-            yv[u] = (k < P && smp < Ns && i0 + u * SLN < 128) ? Xr[(k0 * NC + rr) + ldr * smp] : 0.0;
-        }
+        for (int u = 0; u < 2; u++)
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int i = i0 + u * SLN;
-            if (i >= 128) continue;
-            // y 2^49 as a 64-bit integer (|y| < 1/2: 48 bits), then 7 balanced base-128 digits, least significant first, with
-            // integer shifts and adds (the FP64 round / subtract chain of the first version cost twice the issue slots)
-            long long v = __double2ll_rn(yv[u] * sc49);
-#pragma unroll
-            for (int p = NSL - 1; p >= 1; p--) {
-                const int q = (int)((v + 64) & 127) - 64;
-                v = (v - q) >> 7;
-                tile[(p * ROWS + rr) * LD + i] = (signed char)q;
+            for (int w = 0; w < 4; w++) {
+                const int j = j0 + u * SLN;
+                const int64_t smp = s0 + 4 * j + w;
+                yv[u][w] = (k < P && j < 32 && smp < Ns) ? Xr[(k0 * NC + rr) + ldr * smp] : 0.0;
             }
-            tile[rr * LD + i] = (signed char)v;              // top digit, |v| <= 64
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int j = j0 + u * SLN;
+            if (j >= 32) continue;
+            unsigned word[NSL];
+#pragma unroll
+            for (int p = 0; p < NSL; p++) word[p] = 0u;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                // y 2^49 as a 64-bit integer (|y| < 1/2: 48 bits), then 7 balanced base-128 digits, least significant first
+                long long v = __double2ll_rn(yv[u][w] * sc49);
+#pragma unroll
+                for (int p = NSL - 1; p >= 1; p--) {
+                    const int q = (int)((v + 64) & 127) - 64;
+                    v = (v - q) >> 7;
+                    word[p] |= ((unsigned)q & 0xffu) << (8 * w);
+                }
+                word[0] |= ((unsigned)(int)v & 0xffu) << (8 * w);      // top digit, |v| <= 64
+            }
+#pragma unroll
+            for (int p = 0; p < NSL; p++) *reinterpret_cast<unsigned*>(&tile[(p * ROWS + rr) * LD + 4 * j]) = word[p];
         }
     }
     __syncthreads();
