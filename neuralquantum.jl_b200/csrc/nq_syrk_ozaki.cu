@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
     extern __shared__ signed char tile[];                 // [NSL][32 NC][128 + 4]
     constexpr int ROWS = 32 * NC, LD = 128 + 4;
     const int tid = threadIdx.x;
-    const int64_t k0 = (int64_t)blockIdx.x * 32, s0 = (int64_t)blockIdx.y * 128;
+    // consecutive CTAs sweep the SAMPLE axis of the same rows: their 128-byte output lines are neighbours in memory (with the
+    // row axis fastest every line went to a different DRAM page: 1.74 ms for 4.3 GB)
+    const int64_t k0 = (int64_t)blockIdx.y * 32, s0 = (int64_t)blockIdx.x * 128;
     const int rr = tid % ROWS, sl0 = tid / ROWS;           // real row in the tile, first sample lane
     constexpr int SLN = 256 / ROWS;                        // sample lanes
     const int64_t k = k0 + rr / NC;
@@ -127,8 +129,8 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
         const double m = __longlong_as_double((long long)mx[k]);
         if (m > 0.0) { frexp(m, &e); }                     // m = f 2^e, f in [0.5, 1)
         e += 1;                                            // |x| 2^-e <= 0.5: every digit fits [-64, 64]
-        if (rr % NC == 0 && blockIdx.y == 0 && sl0 == 0) ex[k] = e;
-    } else if (rr % NC == 0 && blockIdx.y == 0 && sl0 == 0 && k < Ppad) {
+        if (rr % NC == 0 && blockIdx.x == 0 && sl0 == 0) ex[k] = e;
+    } else if (rr % NC == 0 && blockIdx.x == 0 && sl0 == 0 && k < Ppad) {
         ex[k] = 0;
     }
     const double sc49 = scalbn(1.0, 7 * NSL - e);          // x 2^-e in (-1/2, 1/2), times 2^49
@@ -531,7 +533,7 @@ int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns,
     const int64_t Nspad = (Ns + 127) / 128 * 128;
     const int neg_plane = (NC == 2 && Wim) ? 1 : 0, NP = NC + neg_plane;
     const int64_t rows_total = (int64_t)NSL * NP * Ppad;
-    if (rows_total > 0x7fffffff || Nspad > 0x7fffffff || Nspad / 128 > 65535) return NQ_OK;
+    if (rows_total > 0x7fffffff || Nspad > 0x7fffffff || Ppad / 32 > 65535) return NQ_OK;
     const size_t obytes = (size_t)rows_total * Nspad;
     signed char* ops = (signed char*)nq_scratch(ctx, SL_W4, obytes);
     if (!ops) { cudaGetLastError(); return NQ_OK; }
@@ -558,7 +560,7 @@ int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns,
         }
     }
     {
-        dim3 g((unsigned)(Ppad / 32), (unsigned)(Nspad / 128));
+        dim3 g((unsigned)(Nspad / 128), (unsigned)(Ppad / 32));
         const size_t smem = (size_t)NSL * 32 * NC * (128 + 4);
         auto ks = oz_split_kernel<NC>;
         NQ_CUDA(ctx, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
