@@ -2071,7 +2071,7 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
     double* Wre = (double*)nq_scratch(ctx, SL_W0, plane * nsplit);
     double* Wim = out_complex ? (double*)nq_scratch(ctx, SL_W1, plane * nsplit) : nullptr;
     if (!Wre || (out_complex && !Wim)) return NQ_ERR_ALLOC;
-    // FP64: the real part runs on the integer tensor cores (Ozaki scheme, nq_syrk_ozaki.cu) from 1024 samples on; NQ_SR_FP64=dmma
+    // FP64: S runs on the integer tensor cores (Ozaki scheme, nq_syrk_ozaki.cu) from 4096 samples on; NQ_SR_FP64=dmma
     // forces the DMMA kernel (which is also the fallback when the digit planes cannot be allocated)
     static const int want_ozaki = [] { const char* e = getenv("NQ_SR_FP64"); return e ? (!strcmp(e, "dmma") ? 0 : 1) : 1; }();
     bool oz = false;
@@ -2079,7 +2079,7 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
     const unsigned long long* known_max = (ctx->rowmax_ptr == Oc && ctx->rowmax_P == P && ctx->rowmax_Ns == Ns && ctx->rowmax_ld == ldO)
                                               ? ctx->rowmax : nullptr;
     ctx->rowmax_ptr = nullptr;
-    if (want_ozaki && nq_dtype_is_double(dtype) && Ns >= 1024) {
+    if (want_ozaki && nq_dtype_is_double(dtype) && Ns >= 4096) {        // below: fixed costs of the pre-pass win (cfg2: 0.34 vs 0.47 ms)
         // its own split of K: every CTA drains its accumulators into the FP64 partial once per pass, so a split should cover
         // >= 2048 samples (the DMMA split above goes down to 128, which at 8 192 samples per GPU made the Ozaki path slower)
         int ns_oz = 1;

@@ -147,7 +147,7 @@ class BatchedSampler:
         from .core import Context
         torch = _torch()
         net, ctx, Ns, P = self.net, self.ctx, self.Ns, self.net.P
-        if self.symm or chunks <= 1 or Ns < 4096 * chunks:
+        if self.symm or chunks <= 1 or Ns < 8192 * chunks:      # measured: 8192 samples per GPU are faster in one piece
             self.set_samples(sigma)
             return self.evaluate()
         dev = torch.device("cuda", ctx.device)

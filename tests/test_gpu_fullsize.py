@@ -148,7 +148,7 @@ def test_pipelined_host_evaluate_is_bit_identical(nq, ctx):
     ref = [t.clone() for t in (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc)]
     for t in (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc):
         t.zero_()
-    bs.evaluate_host(sig, chunks=4)
+    bs.evaluate_host(sig, chunks=2)
     torch.cuda.synchronize()
     for a, b in zip(ref, (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc)):
         assert torch.equal(a, b)

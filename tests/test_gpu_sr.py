@@ -26,7 +26,10 @@ def _rand(rng, shape, dtype):
 @pytest.mark.parametrize("dtype,P,Ns,real_params", [
     (np.complex128, 230, 1000, False), (np.complex128, 576, 2000, True), (np.float64, 130, 515, True),
     (np.complex64, 200, 777, False), (np.float32, 129, 600, True), (np.complex128, 300, 70, False),
-    (np.complex128, 1, 9, False)])
+    (np.complex128, 1, 9, False),
+    # >= 4096 samples: the FP64 S assembly runs on the integer tensor cores (Ozaki scheme, nq_syrk_ozaki.cu): complex S (two
+    # launches), real S of complex rows, real rows; odd sizes exercise the zero padding of rows and samples
+    (np.complex128, 230, 4200, False), (np.complex128, 576, 4500, True), (np.float64, 130, 4100, True)])
 def test_center_force_setup(nq, ctx, dtype, P, Ns, real_params):
     L = nq._lib
     rng = np.random.default_rng(5)
