@@ -280,7 +280,13 @@ int nq_force_ket(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t N
  * Returns the cost <|L_loc|^2> in *cost (host double). */
 int nq_force_liouvillian(nq_ctx_t ctx, const void* Lloc, const void* gLloc, int64_t ld, int64_t P,
                          int64_t Ns, nq_dtype dtype, const void* avg, void* gradC, double* cost);
-/* S and F from the centred O.  real_params != 0: S = Re(Oc Oc^H)/Ns (real [P,P]), F = Re(gradC);
+/* S and F from the centred O.  Implementation (all hand-written, chosen by size and precision):
+ *   FP64, >= 4096 samples: Ozaki scheme on the integer tensor cores (tcgen05 kind::i8; rows scaled by their exponent, 7
+ *     signed 7-bit digits, 34 exact products, FP64 recombination) -- assumes rows without extreme outliers (the digits
+ *     keep 48 bits below the largest entry of a row; gradients of the machines here are bounded); NQ_SR_FP64=dmma in the
+ *     environment forces the FP64 tensor instruction (DMMA), which is also used below 4096 samples and as the fallback;
+ *   FP32 mode: 3xTF32 on tcgen05 fed by TMA (NQ_SR_TF32=stage: the staging kernel), split-K partials summed in FP64.
+ * real_params != 0: S = Re(Oc Oc^H)/Ns (real [P,P]), F = Re(gradC);
  * else S = conj(Oc Oc^H)/Ns (complex), F = gradC.  Ns_total = global sample count used to
  * normalise (== Ns on one GPU; under sharding the partial S is all-reduced by the caller, quirk Q5).
  * ref: SR/SRDirect.jl:26-49, SRIterative.jl:45-62 */
