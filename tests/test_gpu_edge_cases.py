@@ -125,3 +125,30 @@ def test_argument_errors_are_statuses(nq, ctx):
     assert st == L.NQ_ERR_NOT_POSDEF
     with pytest.raises(nq.PosDefException):
         L.check(st, ctx.h)
+
+
+@pytest.mark.parametrize("dtype,P,Ns,ld,real_params", [(np.complex128, 37, 4200, 64, False), (np.complex64, 37, 4200, 64, True),
+                                                       (np.float64, 130, 150000, 130, True)])
+def test_tensor_core_s_assembly_shapes(nq, ctx, dtype, P, Ns, ld, real_params):
+    """The tcgen05 S-assembly paths (FP64: Ozaki digits on kind::i8; FP32 mode: TMA-fed 3xTF32) on awkward shapes: a padded
+    leading dimension (rows P..ld-1 hold garbage that must not enter S), sizes that are not multiples of the 128-row tiles or
+    the 64-sample boxes, and a K so long that one CTA drains its int32 accumulators several times (150 000 samples in one
+    split: three accumulation windows)."""
+    L = nq._lib
+    rng = np.random.default_rng(23)
+    dtype = np.dtype(dtype)
+    cplx = dtype.kind == "c"
+    O = rng.standard_normal((P, Ns)) + (1j * rng.standard_normal((P, Ns)) if cplx else 0.0)
+    O = (O - O.mean(axis=1, keepdims=True)).astype(dtype)
+    pad = np.full((ld, Ns), 1e6, dtype=dtype, order="F")
+    pad[:P] = O
+    d = torch.from_numpy(np.ascontiguousarray(pad.T)).cuda()
+    single = dtype in (np.dtype(np.float32), np.dtype(np.complex64))
+    sdt = np.dtype(dtype if (cplx and not real_params) else (np.float32 if single else np.float64))
+    S = np.zeros((P, P), sdt, order="F")
+    F = np.zeros(P, sdt)
+    g = np.ones(P, np.complex64 if single else np.complex128)
+    L.check(L.lib.nq_sr_setup(ctx.h, d.data_ptr(), ld, P, Ns, Ns, L.nq_dtype(dtype), L.ptr(g), int(real_params), L.ptr(S), L.ptr(F)), ctx.h)
+    O64 = O.astype(np.complex128 if cplx else np.float64)
+    rS, _ = OSR.sr_setup(O64, g.astype(np.complex128), real_params)
+    H.assert_close(S, rS, H.TOL[dtype], "S")
