@@ -272,6 +272,14 @@ int nq_exact_sample(nq_machine_t m, const double* cdf, uint64_t seed, int64_t ch
  * ==================================================================================== */
 /* <O> and O <- O - <O> in place.  ref: BaseIterativeSampler.jl:19-26.  avg [P] */
 int nq_center(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype, void* avg);
+/* The same with the subtraction DEFERRED when the next consumer can do it on the fly: avg is returned, and if
+ * *deferred = 1 the matrix is left uncentred -- the FP64 S assembly of nq_sr_setup (integer tensor-core path) then subtracts
+ * the means while it slices the rows, which saves the read-modify-write pass over O; any other nq_sr_setup path centres in
+ * place first.  Device-resident FP64 O with >= 4096 samples only (otherwise it is nq_center and *deferred = 0).
+ * nq_center_finish applies a pending subtraction (no-op if none is pending for this matrix): call it before reading O as
+ * the centred matrix (nq_force_ket, matrix-free solves).  ref: BaseIterativeSampler.jl:19-26 */
+int nq_center_lazy(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype, void* avg, int* deferred);
+int nq_center_finish(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype);
 /* gradC = E_loc * Oc' / Ns  (F_k = <E_loc conj(Oc_k)>).  ref: BatchedValSampler.jl:97-115.
  * Eloc [Ns] complex of matching precision; gradC [P] complex */
 int nq_force_ket(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype,

@@ -522,6 +522,16 @@ end
 sr_finish!(ctx::Ctx, Sacc, sumO, P::Integer, Ns_total::Integer, T::Type, real_params::Bool) =
     check(ctx, ccall((:nq_sr_finish, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Cint, Cint),
                      ctx.h, Sacc, sumO, P, Ns_total, nqdtype(T), real_params ? 1 : 0))
+# centring with the subtraction deferred to the S assembly (returns true when O was left uncentred), and its completion
+function center_gradient_lazy!(ctx::Ctx, O::AbstractMatrix, avg::AbstractVector)
+    flag = Ref{Cint}(0)
+    check(ctx, ccall((:nq_center_lazy, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Cint, Ptr{Cvoid}, Ptr{Cint}),
+                     ctx.h, O, size(O, 1), size(O, 1), size(O, 2), nqdtype(O), avg, flag))
+    return flag[] != 0
+end
+center_finish!(ctx::Ctx, O::AbstractMatrix) =
+    check(ctx, ccall((:nq_center_finish, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Cint),
+                     ctx.h, O, size(O, 1), size(O, 1), size(O, 2), nqdtype(O)))
 # structure of the gradient rows known to the caller (NDM: lambda rows real, mu rows imaginary): one-shot hint for the next setup
 sr_hint_row_planes!(ctx::Ctx, planes::Vector{UInt8}) =
     check(ctx, ccall((:nq_sr_hint_row_planes, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), ctx.h, planes, length(planes)))

@@ -40,6 +40,17 @@ struct nq_ctx_s {
     int64_t rowmax_cap = 0;
     const void* rowmax_ptr = nullptr;
     int64_t rowmax_P = 0, rowmax_Ns = 0, rowmax_ld = 0;
+    // deferred centring (nq_center_lazy): the means were computed but NOT subtracted; rowmax then holds the maxima of the
+    // UNcentred rows and `shift` the means (device, complex128 [P]); the next nq_sr_setup on the same matrix either lets the
+    // Ozaki pre-pass subtract on the fly or subtracts in place first
+    void* shift = nullptr;
+    int64_t shift_cap = 0;
+    bool shift_pending = false;            // stays set until the subtraction happened (nq_center_finish, an S path that centres
+    const void* shift_ptr = nullptr;       // in place) or the matrix is re-centred / rewritten by a machine kernel
+    int64_t shift_P = 0, shift_Ns = 0, shift_ld = 0;
+    bool shift_matches(const void* X, int64_t ld, int64_t P, int64_t Ns) const {
+        return shift_pending && shift_ptr == X && shift_P == P && shift_Ns == Ns && shift_ld == ld;
+    }
 };
 
 int nq_fail(nq_ctx_t ctx, int code, const char* fmt, ...);

@@ -85,6 +85,7 @@ extern "C" int nq_ctx_destroy(nq_ctx_t ctx) {
     nq_comm_destroy(ctx);
     for (auto& s : ctx->slots) if (s.p) cudaFree(s.p);
     if (ctx->rowmax) cudaFree(ctx->rowmax);
+    if (ctx->shift) cudaFree(ctx->shift);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return NQ_OK;

@@ -73,4 +73,5 @@ int nq_syrk_tf32_device(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, in
                         bool out_complex, void* dS);
 // nq_syrk_ozaki.cu: FP64 S assembly (real part) on the integer tensor cores; *used = false -> run the DMMA kernel instead
 int nq_syrk_ozaki_device(nq_ctx_t ctx, const double* Xr, int64_t ldr, int64_t P, int64_t Ns, int NC, int ntile, int nsplit, double* W,
-                         double* Wim, const unsigned long long* known_rowmax, bool* used);
+                         double* Wim, const unsigned long long* known_rowmax, const double* shift /* complex128 [P] or NULL */,
+                         bool* used);

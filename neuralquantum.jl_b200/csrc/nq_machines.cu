@@ -449,6 +449,7 @@ int dispatch_rbm(nq_machine_t m, const uint64_t* prow, const uint64_t* pcol, int
 int nq_machine_eval_device(nq_machine_t m, const uint64_t* prow, const uint64_t* pcol, int64_t B,
                            void* out, void* O, int64_t ldO) {
     if (B == 0) return NQ_OK;
+    if (O) { m->ctx->shift_pending = false; m->ctx->rowmax_ptr = nullptr; }     // new rows: records of a centring pass are stale
     if (m->kind == NQ_NDM) {
         if (m->dtype == NQ_F64)
             return m->act == NQ_SOFTPLUS ? launch_ndm<double, NQ_SOFTPLUS>(m, prow, pcol, B, out, O, ldO)

@@ -517,6 +517,7 @@ extern "C" int nq_logpsi_grad_local_packed(nq_machine_t m, nq_operator_t op, con
     if (!nq_is_device_ptr(prow) || !nq_is_device_ptr(O) || !nq_is_device_ptr(out_logpsi) || !nq_is_device_ptr(out_loc) ||
         (out_gloc && !nq_is_device_ptr(out_gloc)))
         return nq_fail(ctx, NQ_ERR_ARG, "the fused entry point works on device-resident buffers");
+    ctx->shift_pending = false; ctx->rowmax_ptr = nullptr;          // new rows: records of a centring pass are stale
     return nq_local_device(m, op, prow, pcol, B, out_logpsi, O, ldO, out_loc, out_gloc, ld);
 }
 

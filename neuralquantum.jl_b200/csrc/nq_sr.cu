@@ -45,15 +45,17 @@ __device__ __forceinline__ void dd_fma(dd& a, double x, double y) { // a += x * 
 template <typename E, bool CONJ>
 __global__ void colsum_partial_kernel(const E* __restrict__ X, int64_t ld, int64_t P, int64_t Ns,
                                       const cx<typename elem_traits<E>::real>* __restrict__ w,
-                                      cxd* __restrict__ partial, cxd* __restrict__ partial_lo) {
+                                      cxd* __restrict__ partial, cxd* __restrict__ partial_lo, unsigned long long* __restrict__ mx) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= P) return;
     int64_t per = (Ns + gridDim.y - 1) / gridDim.y;
     int64_t s0 = blockIdx.y * per, s1 = s0 + per < Ns ? s0 + per : Ns;
     dd ar = {0.0, 0.0}, ai = {0.0, 0.0};
+    double m = 0.0;
     for (int64_t s = s0; s < s1; s++) {
         E x = X[k + ld * s];
         double xr = (double)real_part(x), xi = (double)imag_part(x);
+        m = fmax(m, fmax(fabs(xr), fabs(xi)));
         if (CONJ) xi = -xi;
         if (w) {
             double wr = (double)w[s].re, wi = (double)w[s].im;
@@ -63,6 +65,7 @@ __global__ void colsum_partial_kernel(const E* __restrict__ X, int64_t ld, int64
     }
     partial[blockIdx.y * P + k] = cxd(ar.hi, ai.hi);
     partial_lo[blockIdx.y * P + k] = cxd(ar.lo, ai.lo);
+    if (mx) atomicMax(&mx[k], (unsigned long long)__double_as_longlong(m));
 }
 
 // fixed-order compensated reduction of the slices: 8 threads per row take the slices g, g + 8, ... and their partial
@@ -91,7 +94,8 @@ __global__ void colsum_final_kernel(const cxd* __restrict__ partial, const cxd* 
 }
 
 template <typename E, bool CONJ>
-int colsum(nq_ctx_t ctx, const void* X, int64_t ld, int64_t P, int64_t Ns, const void* w, double scale, cxd* out) {
+int colsum(nq_ctx_t ctx, const void* X, int64_t ld, int64_t P, int64_t Ns, const void* w, double scale, cxd* out,
+           unsigned long long* mx = nullptr) {
     int nslice = (int)std::min<int64_t>(std::max<int64_t>(1, Ns / 256), 4 * (int64_t)ctx->num_sms * 8 / std::max<int64_t>(1, (P + 127) / 128));
     nslice = std::max(1, std::min(nslice, 1024));
     cxd* partial = (cxd*)nq_scratch(ctx, SL_W5, (size_t)2 * nslice * P * sizeof(cxd));
@@ -99,19 +103,19 @@ int colsum(nq_ctx_t ctx, const void* X, int64_t ld, int64_t P, int64_t Ns, const
     cxd* partial_lo = partial + (size_t)nslice * P;
     dim3 grid((unsigned)((P + 127) / 128), (unsigned)nslice);
     NQ_LAUNCH(ctx, (colsum_partial_kernel<E, CONJ>), grid, 128, 0, (const E*)X, ld, P, Ns,
-              (const cx<typename elem_traits<E>::real>*)w, partial, partial_lo);
+              (const cx<typename elem_traits<E>::real>*)w, partial, partial_lo, mx);
     NQ_LAUNCH(ctx, colsum_final_kernel<E>, (unsigned)((P + 31) / 32), 256, 0, (const cxd*)partial, (const cxd*)partial_lo, nslice, P, scale, out);
     return NQ_OK;
 }
 
 template <bool CONJ>
 int colsum_dispatch(nq_ctx_t ctx, nq_dtype dtype, const void* X, int64_t ld, int64_t P, int64_t Ns, const void* w,
-                    double scale, cxd* out) {
+                    double scale, cxd* out, unsigned long long* mx = nullptr) {
     switch (dtype) {
-        case NQ_F32: return colsum<float, CONJ>(ctx, X, ld, P, Ns, w, scale, out);
-        case NQ_F64: return colsum<double, CONJ>(ctx, X, ld, P, Ns, w, scale, out);
-        case NQ_C64: return colsum<cxf, CONJ>(ctx, X, ld, P, Ns, w, scale, out);
-        default: return colsum<cxd, CONJ>(ctx, X, ld, P, Ns, w, scale, out);
+        case NQ_F32: return colsum<float, CONJ>(ctx, X, ld, P, Ns, w, scale, out, mx);
+        case NQ_F64: return colsum<double, CONJ>(ctx, X, ld, P, Ns, w, scale, out, mx);
+        case NQ_C64: return colsum<cxf, CONJ>(ctx, X, ld, P, Ns, w, scale, out, mx);
+        default: return colsum<cxd, CONJ>(ctx, X, ld, P, Ns, w, scale, out, mx);
     }
 }
 
@@ -1910,9 +1914,23 @@ static const void* sr_matrix_on_device(nq_ctx_t ctx, int slot, const void* X, in
     return d;
 }
 
-extern "C" int nq_center(nq_ctx_t ctx, void* O_user, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype, void* avg) {
+static int launch_subtract(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype, const cxd* a, unsigned long long* mx) {
+    dim3 grid((unsigned)((P + 127) / 128), (unsigned)std::min<int64_t>(Ns, 4096));
+    switch (dtype) {
+        case NQ_F32: NQ_LAUNCH(ctx, subtract_avg_kernel<float>, grid, 128, 0, (float*)O, ldO, P, Ns, a, mx); break;
+        case NQ_F64: NQ_LAUNCH(ctx, subtract_avg_kernel<double>, grid, 128, 0, (double*)O, ldO, P, Ns, a, mx); break;
+        case NQ_C64: NQ_LAUNCH(ctx, subtract_avg_kernel<cxf>, grid, 128, 0, (cxf*)O, ldO, P, Ns, a, mx); break;
+        default: NQ_LAUNCH(ctx, subtract_avg_kernel<cxd>, grid, 128, 0, (cxd*)O, ldO, P, Ns, a, mx); break;
+    }
+    return NQ_OK;
+}
+
+// lazy != NULL: the subtraction may be deferred (*lazy = 1): the means are returned, O is left as it is, and the context keeps
+// (maxima of the uncentred rows, means) for the next nq_sr_setup on this matrix; nq_center_finish applies the subtraction
+static int center_impl(nq_ctx_t ctx, void* O_user, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype, void* avg, int* lazy) {
     if (!ctx || !O_user || !avg || P <= 0 || Ns <= 0 || ldO < P) return NQ_ERR_ARG;
     NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (lazy) *lazy = 0;
     int hs = NQ_OK;
     void* O = const_cast<void*>(sr_matrix_on_device(ctx, SL_HOSTO, O_user, ldO, Ns, dtype, &hs));
     if (hs != NQ_OK) return hs;
@@ -1921,7 +1939,11 @@ extern "C" int nq_center(nq_ctx_t ctx, void* O_user, int64_t ldO, int64_t P, int
     void* davg = st.out(SL_OUT0, avg, (size_t)P * nq_dtype_size(dtype));
     cxd* a = (cxd*)nq_scratch(ctx, SL_W0, (size_t)P * sizeof(cxd));
     if (!a || st.status != NQ_OK) return NQ_ERR_ALLOC;
-    NQ_CHECK(colsum_dispatch<false>(ctx, dtype, O, ldO, P, Ns, nullptr, 1.0, a));
+    // deferral only pays when the next consumer is the Ozaki S assembly (FP64, device-resident, >= 4096 samples)
+    const bool defer = lazy && nq_dtype_is_double(dtype) && !o_on_host && Ns >= 4096;
+    unsigned long long* mx_raw = defer ? rowmax_arm(ctx, O, ldO, P, Ns) : nullptr;
+    ctx->shift_pending = false;
+    NQ_CHECK(colsum_dispatch<false>(ctx, dtype, O, ldO, P, Ns, nullptr, 1.0, a, mx_raw));
     // under sharding: <O> is the global mean (C1, BaseIterativeSampler.jl:23)
     if (ctx->nccl_comm) {
         NQ_CHECK(nq_allreduce_device(ctx, a, P, NQ_C128, false));
@@ -1934,20 +1956,50 @@ extern "C" int nq_center(nq_ctx_t ctx, void* O_user, int64_t ldO, int64_t P, int
         NQ_LAUNCH(ctx, colsum_final_kernel<double>, (unsigned)((P + 31) / 32), 256, 0, (const cxd*)a, (const cxd*)nullptr, 1, P, 1.0 / (double)ns_tot, tmp);
         a = tmp;
     }
-    dim3 grid((unsigned)((P + 127) / 128), (unsigned)std::min<int64_t>(Ns, 4096));
-    unsigned long long* mx = (nq_dtype_is_double(dtype) && !o_on_host) ? rowmax_arm(ctx, O, ldO, P, Ns) : nullptr;
-    switch (dtype) {
-        case NQ_F32: NQ_LAUNCH(ctx, subtract_avg_kernel<float>, grid, 128, 0, (float*)O, ldO, P, Ns, (const cxd*)a, mx); break;
-        case NQ_F64: NQ_LAUNCH(ctx, subtract_avg_kernel<double>, grid, 128, 0, (double*)O, ldO, P, Ns, (const cxd*)a, mx); break;
-        case NQ_C64: NQ_LAUNCH(ctx, subtract_avg_kernel<cxf>, grid, 128, 0, (cxf*)O, ldO, P, Ns, (const cxd*)a, mx); break;
-        default: NQ_LAUNCH(ctx, subtract_avg_kernel<cxd>, grid, 128, 0, (cxd*)O, ldO, P, Ns, (const cxd*)a, mx); break;
+    bool deferred = false;
+    if (defer && mx_raw) {
+        if (ctx->shift_cap < P) {
+            if (ctx->shift) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->shift); ctx->shift = nullptr; ctx->shift_cap = 0; }
+            if (cudaMalloc(&ctx->shift, (size_t)(P + P / 4 + 64) * sizeof(cxd)) == cudaSuccess) ctx->shift_cap = P + P / 4 + 64;
+            else cudaGetLastError();
+        }
+        if (ctx->shift_cap >= P) {
+            NQ_CUDA(ctx, cudaMemcpyAsync(ctx->shift, a, (size_t)P * sizeof(cxd), cudaMemcpyDeviceToDevice, ctx->stream));
+            ctx->shift_pending = true;
+            ctx->shift_ptr = O; ctx->shift_P = P; ctx->shift_Ns = Ns; ctx->shift_ld = ldO;
+            deferred = true;
+        }
     }
+    if (!deferred) {
+        unsigned long long* mx = (nq_dtype_is_double(dtype) && !o_on_host) ? rowmax_arm(ctx, O, ldO, P, Ns) : nullptr;
+        NQ_CHECK(launch_subtract(ctx, O, ldO, P, Ns, dtype, (const cxd*)a, mx));
+    }
+    if (lazy) *lazy = deferred ? 1 : 0;
     NQ_LAUNCH(ctx, convert_from_cxd_kernel, (unsigned)((P + 255) / 256), 256, 0, (const cxd*)a, davg, P, (int)dtype, 0);
     if (o_on_host) {      // centred O goes back to the caller's array (the reference centres in place)
         NQ_CUDA(ctx, cudaMemcpyAsync(O_user, O, (size_t)ldO * Ns * nq_dtype_size(dtype), cudaMemcpyDeviceToHost, ctx->stream));
         NQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return st.finish();
+}
+
+extern "C" int nq_center(nq_ctx_t ctx, void* O_user, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype, void* avg) {
+    return center_impl(ctx, O_user, ldO, P, Ns, dtype, avg, nullptr);
+}
+
+extern "C" int nq_center_lazy(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype, void* avg, int* deferred) {
+    if (!deferred) return NQ_ERR_ARG;
+    return center_impl(ctx, O, ldO, P, Ns, dtype, avg, deferred);
+}
+
+// the subtraction a deferred nq_center_lazy left out (no-op when nothing is pending for this matrix)
+extern "C" int nq_center_finish(nq_ctx_t ctx, void* O, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype) {
+    if (!ctx || !O || P <= 0 || Ns <= 0 || ldO < P) return NQ_ERR_ARG;
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->shift_matches(O, ldO, P, Ns)) return NQ_OK;
+    ctx->shift_pending = false;
+    ctx->rowmax_ptr = nullptr;             // the recorded maxima belong to the uncentred rows
+    return launch_subtract(ctx, O, ldO, P, Ns, dtype, (const cxd*)ctx->shift, nullptr);
 }
 
 extern "C" int nq_force_ket(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P, int64_t Ns, nq_dtype dtype,
@@ -2076,10 +2128,18 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
     static const int want_ozaki = [] { const char* e = getenv("NQ_SR_FP64"); return e ? (!strcmp(e, "dmma") ? 0 : 1) : 1; }();
     bool oz = false;
     // row maxima left by the centring pass of this very matrix (one-shot): the Ozaki pre-pass skips its own read of O
-    const unsigned long long* known_max = (ctx->rowmax_ptr == Oc && ctx->rowmax_P == P && ctx->rowmax_Ns == Ns && ctx->rowmax_ld == ldO)
-                                              ? ctx->rowmax : nullptr;
+    const bool rec = ctx->rowmax_ptr == Oc && ctx->rowmax_P == P && ctx->rowmax_Ns == Ns && ctx->rowmax_ld == ldO;
+    const unsigned long long* known_max = rec ? ctx->rowmax : nullptr;
+    // deferred centring of this matrix (nq_center_lazy): stays pending while the rows stay uncentred
+    const cxd* shift = ctx->shift_matches(Oc, ldO, P, Ns) ? (const cxd*)ctx->shift : nullptr;
     ctx->rowmax_ptr = nullptr;
-    if (want_ozaki && nq_dtype_is_double(dtype) && Ns >= 4096) {        // below: fixed costs of the pre-pass win (cfg2: 0.34 vs 0.47 ms)
+    const bool ozaki_ok = want_ozaki && nq_dtype_is_double(dtype) && Ns >= 4096;
+    if (shift && !ozaki_ok) {            // nobody to subtract on the fly: centre in place now
+        NQ_CHECK(launch_subtract(ctx, const_cast<void*>(Oc), ldO, P, Ns, dtype, shift, nullptr));
+        ctx->shift_pending = false;
+        shift = nullptr; known_max = nullptr;
+    }
+    if (ozaki_ok) {        // below: fixed costs of the pre-pass win (cfg2: 0.34 vs 0.47 ms)
         // its own split of K: every CTA drains its accumulators into the FP64 partial once per pass, so a split should cover
         // >= 2048 samples (the DMMA split above goes down to 128, which at 8 192 samples per GPU made the Ozaki path slower)
         int ns_oz = 1;
@@ -2091,8 +2151,12 @@ extern "C" int nq_sr_setup(nq_ctx_t ctx, const void* Oc, int64_t ldO, int64_t P,
             if ((waves >= 1.0 || ns == 1) && cost < best) { best = cost; ns_oz = ns; }
         }
         NQ_CHECK(nq_syrk_ozaki_device(ctx, (const double*)Oc, ldr, P, Ns, ocx ? 2 : 1, ntile, ns_oz, Wre, out_complex ? Wim : nullptr,
-                                      known_max, &oz));
+                                      known_max, (const double*)shift, &oz));
         if (oz) nsplit = ns_oz;
+        else if (shift) {                                                                                           // fallback path
+            NQ_CHECK(launch_subtract(ctx, const_cast<void*>(Oc), ldO, P, Ns, dtype, shift, nullptr));
+            ctx->shift_pending = false;
+        }
     }
     if (ocx) {
         if (nq_dtype_is_double(dtype)) {

@@ -114,6 +114,7 @@ __global__ void oz_activity_kernel(const double* __restrict__ Xr, int64_t ldr, i
 template <int NC>
 __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, int64_t Ppad,
                                                        int64_t Nspad, const unsigned long long* __restrict__ mx,
+                                                       const double* __restrict__ shift /* (re, im) per row or NULL */,
                                                        signed char* __restrict__ out, int* __restrict__ ex, int neg_plane) {
     extern __shared__ signed char tile[];                 // [NSL][32 NC][128 + 4]
     constexpr int ROWS = 32 * NC, LD = 128 + 4;
@@ -125,8 +126,11 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
     constexpr int SLN = 256 / ROWS;                        // sample lanes
     const int64_t k = k0 + rr / NC;
     int e = 0;
+    // deferred centring: the values are x - shift; mx then bounds the UNcentred row, |shift| is added to the bound
+    const double sh = (shift && k < P) ? shift[2 * k + (NC == 2 ? rr % NC : 0)] : 0.0;
     if (k < P) {
-        const double m = __longlong_as_double((long long)mx[k]);
+        double m = __longlong_as_double((long long)mx[k]);
+        if (shift) m += fmax(fabs(shift[2 * k]), fabs(shift[2 * k + 1]));
         if (m > 0.0) { frexp(m, &e); }                     // m = f 2^e, f in [0.5, 1)
         e += 1;                                            // |x| 2^-e <= 0.5: every digit fits [-64, 64]
         if (rr % NC == 0 && blockIdx.x == 0 && sl0 == 0) ex[k] = e;
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
             for (int w = 0; w < 4; w++) {
                 const int j = j0 + u * SLN;
                 const int64_t smp = s0 + 4 * j + w;
-                yv[u][w] = (k < P && j < 32 && smp < Ns) ? Xr[(k0 * NC + rr) + ldr * smp] : 0.0;
+                yv[u][w] = (k < P && j < 32 && smp < Ns) ? Xr[(k0 * NC + rr) + ldr * smp] - sh : 0.0;
             }
 #pragma unroll
         for (int u = 0; u < 2; u++) {
@@ -525,7 +529,7 @@ PFN_cuTensorMapEncodeTiled get_encode() {
 
 template <int NC>
 int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns, int ntile, int nsplit, double* W, double* Wim,
-              const unsigned long long* known_rowmax, bool* used) {
+              const unsigned long long* known_rowmax, const double* shift, bool* used) {
     *used = false;
     PFN_cuTensorMapEncodeTiled encode = get_encode();
     if (!encode) return NQ_OK;
@@ -553,6 +557,10 @@ int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns,
         if (NC == 2) {
             if (ctx->hint_P == P && (int)ctx->hint_tile_flags.size() == ntile) {
                 NQ_CUDA(ctx, cudaMemcpyAsync(flags, ctx->hint_tile_flags.data(), (size_t)ntile * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+            } else if (shift) {
+                // deferred centring without a structural hint: a plane that is zero in THIS shard may have a non-zero global
+                // mean, so no plane is skipped (0x03 in every byte = both bits of every tile word)
+                NQ_CUDA(ctx, cudaMemsetAsync(flags, 0x03, (size_t)ntile * sizeof(unsigned), ctx->stream));
             } else {
                 NQ_CUDA(ctx, cudaMemsetAsync(flags, 0, (size_t)ntile * sizeof(unsigned), ctx->stream));
                 NQ_LAUNCH(ctx, oz_activity_kernel<NC>, g, 256, 0, X, ldr, P, Ns, flags);
@@ -564,7 +572,7 @@ int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns,
         const size_t smem = (size_t)NSL * 32 * NC * (128 + 4);
         auto ks = oz_split_kernel<NC>;
         NQ_CUDA(ctx, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NQ_LAUNCH(ctx, ks, g, 256, smem, X, ldr, P, Ns, Ppad, Nspad, (const unsigned long long*)mx, ops, ex, neg_plane);
+        NQ_LAUNCH(ctx, ks, g, 256, smem, X, ldr, P, Ns, Ppad, Nspad, (const unsigned long long*)mx, shift, ops, ex, neg_plane);
     }
     CUtensorMap mapA, mapB;
     {
@@ -614,7 +622,7 @@ int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns,
 // Xr [(k NC + c) + ldr s].  *used = false when the path is not available (no driver entry point, not enough memory for the
 // digit planes): the caller runs the DMMA kernel instead.
 int nq_syrk_ozaki_device(nq_ctx_t ctx, const double* Xr, int64_t ldr, int64_t P, int64_t Ns, int NC, int ntile, int nsplit, double* W,
-                         double* Wim, const unsigned long long* known_rowmax, bool* used) {
-    if (NC == 2) return run_ozaki<2>(ctx, Xr, ldr, P, Ns, ntile, nsplit, W, Wim, known_rowmax, used);
-    return run_ozaki<1>(ctx, Xr, ldr, P, Ns, ntile, nsplit, W, nullptr, known_rowmax, used);
+                         double* Wim, const unsigned long long* known_rowmax, const double* shift, bool* used) {
+    if (NC == 2) return run_ozaki<2>(ctx, Xr, ldr, P, Ns, ntile, nsplit, W, Wim, known_rowmax, shift, used);
+    return run_ozaki<1>(ctx, Xr, ldr, P, Ns, ntile, nsplit, W, nullptr, known_rowmax, shift, used);
 }

@@ -118,6 +118,8 @@ _PROTOS = {
     "nq_exact_table": (_i32, [_vp, _vp]),
     "nq_exact_sample": (_i32, [_vp, _vp, _u64, _i64, _u64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "nq_center": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp]),
+    "nq_center_lazy": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, C.POINTER(_i32)]),
+    "nq_center_finish": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32]),
     "nq_force_ket": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),
     "nq_force_liouvillian": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, C.POINTER(_dbl)]),
     "nq_sr_setup": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _i32, _vp, _vp]),

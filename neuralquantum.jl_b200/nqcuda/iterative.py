@@ -71,7 +71,8 @@ class BatchedSampler:
         self.prow = torch.zeros((self.L, self.B, W), dtype=torch.int64, device=dev)
         self.pcol = torch.zeros_like(self.prow) if net.doubled else None
         self.logpsi = torch.zeros(Ns, dtype=ot, device=dev)
-        self.O = torch.zeros((Ns, P), dtype=ot, device=dev)            # = [P, Ns] column-major
+        self._O = torch.zeros((Ns, P), dtype=ot, device=dev)           # = [P, Ns] column-major; see the `O` property
+        self._center_pending = False
         self.loc = torch.zeros(Ns, dtype=ct, device=dev)
         self.gloc = torch.zeros((Ns, P), dtype=ct, device=dev) if self.is_liouvillian else None
         # symmetrised machines (NDMSymm): the kernels write rows of the BARE net, symmetrised into O / gloc afterwards
@@ -100,6 +101,17 @@ class BatchedSampler:
         self.cost = None
         self.last_iters = 0
 
+    @property
+    def O(self):
+        """The gradient rows [Ns, P] (= [P, Ns] column-major): as written by evaluate(), centred after assemble().  The
+        Liouvillian + explicit-S iteration defers the subtraction of <O> (nq_center_lazy: the S assembly subtracts on the fly
+        and nothing else reads the centred rows); reading this attribute applies a pending subtraction first."""
+        if self._center_pending:
+            L.check(L.lib.nq_center_finish(self.ctx.h, self._O.data_ptr(), self.net.P, self.net.P, self.Ns,
+                                           L.nq_dtype(self.net.out_dtype)), self.ctx.h)
+            self._center_pending = False
+        return self._O
+
     # ---- the hot path -----------------------------------------------------------------
     def sample_states(self):
         """_sample_state!: re-randomise the chains, burn, fill the L slices."""
@@ -125,18 +137,19 @@ class BatchedSampler:
     def evaluate(self):
         """logpsi_and_grad! + local estimator on the stored samples (one fused pass)."""
         net, ctx, Ns = self.net, self.ctx, self.Ns
+        self._center_pending = False          # new rows are about to be written
         pc = self.pcol.data_ptr() if self.pcol is not None else None
         gl = self.gloc.data_ptr() if self.is_liouvillian else None
         if self.symm:       # logpsi_and_grad!(::NDMSymm): bare rows, then symmetrize_grad_NDM_batched! (NDMSymmBatched.jl:16-36)
             glb = self.gloc_bare.data_ptr() if self.is_liouvillian else None
             L.check(L.lib.nq_logpsi_grad_local_packed(net.h, self.op.h, self.prow.data_ptr(), pc, Ns, self.logpsi.data_ptr(),
                                                       self.O_bare.data_ptr(), net.Pb, self.loc.data_ptr(), glb, net.Pb), ctx.h)
-            net.symmetrize(self.O_bare.data_ptr(), net.Pb, Ns, self.O.data_ptr(), net.P)
+            net.symmetrize(self.O_bare.data_ptr(), net.Pb, Ns, self._O.data_ptr(), net.P)
             if self.is_liouvillian:
                 net.symmetrize(glb, net.Pb, Ns, gl, net.P)
             return
         L.check(L.lib.nq_logpsi_grad_local_packed(net.h, self.op.h, self.prow.data_ptr(), pc, Ns, self.logpsi.data_ptr(),
-                                                  self.O.data_ptr(), net.P, self.loc.data_ptr(), gl, net.P), ctx.h)
+                                                  self._O.data_ptr(), net.P, self.loc.data_ptr(), gl, net.P), ctx.h)
 
     def evaluate_host(self, sigma, chunks=2):
         """set_samples + evaluate for HOST configurations [N, B, L] (pinned memory makes the copies asynchronous), software
@@ -160,7 +173,8 @@ class BatchedSampler:
         main_stream = ctx.torch_stream()
         bufs = [self.prow, self.pcol][:len(hosts)]
         W = self.prow.shape[-1]
-        es, cs = self.O.element_size(), self.loc.element_size()
+        es, cs = self._O.element_size(), self.loc.element_size()
+        self._center_pending = False
         fcode = L.nq_dtype(np.dtype(str(hosts[0].dtype).replace("torch.", "")))
         bounds = [(Ns * c) // chunks for c in range(chunks + 1)]
         side_stream.wait_stream(main_stream)                       # the staging / packed buffers may still be read by earlier work
@@ -178,7 +192,7 @@ class BatchedSampler:
             pc = self.pcol.data_ptr() + c0 * W * 8 if self.pcol is not None else None
             gl = self.gloc.data_ptr() + c0 * P * cs if self.is_liouvillian else None
             L.check(L.lib.nq_logpsi_grad_local_packed(net.h, self.op.h, self.prow.data_ptr() + c0 * W * 8, pc, n,
-                                                      self.logpsi.data_ptr() + c0 * es, self.O.data_ptr() + c0 * P * es, P,
+                                                      self.logpsi.data_ptr() + c0 * es, self._O.data_ptr() + c0 * P * es, P,
                                                       self.loc.data_ptr() + c0 * cs, gl, P), ctx.h)
 
     def assemble(self):
@@ -187,7 +201,13 @@ class BatchedSampler:
         oc = L.nq_dtype(net.out_dtype)
         cc = L.nq_dtype(net.cdtype)
         ctx.set_global_samples(self.Ns_total if self.nranks > 1 else 0)
-        L.check(L.lib.nq_center(ctx.h, self.O.data_ptr(), P, P, Ns, oc, self.avg.data_ptr()), ctx.h)
+        if self.is_liouvillian and self.S is not None:
+            # nothing but the S assembly reads the centred rows in this iteration: the subtraction may be deferred
+            flag = C.c_int(0)
+            L.check(L.lib.nq_center_lazy(ctx.h, self._O.data_ptr(), P, P, Ns, oc, self.avg.data_ptr(), C.byref(flag)), ctx.h)
+            self._center_pending = bool(flag.value)
+        else:
+            L.check(L.lib.nq_center(ctx.h, self._O.data_ptr(), P, P, Ns, oc, self.avg.data_ptr()), ctx.h)
         if self.is_liouvillian:
             cost = C.c_double()
             L.check(L.lib.nq_force_liouvillian(ctx.h, self.loc.data_ptr(), self.gloc.data_ptr(), P, P, Ns, cc,
@@ -199,7 +219,7 @@ class BatchedSampler:
         if self.S is not None:
             if self.row_planes is not None:
                 L.check(L.lib.nq_sr_hint_row_planes(ctx.h, L.ptr(self.row_planes), P), ctx.h)
-            L.check(L.lib.nq_sr_setup(ctx.h, self.O.data_ptr(), P, P, Ns, self.Ns_total, oc, self.gradC.data_ptr(),
+            L.check(L.lib.nq_sr_setup(ctx.h, self._O.data_ptr(), P, P, Ns, self.Ns_total, oc, self.gradC.data_ptr(),
                                       int(self.real_params), self.S.data_ptr(), self.F.data_ptr()), ctx.h)
             if self.nranks > 1:      # C4 (global mean, quirk Q5)
                 ctx.allreduce_sum(self.S.data_ptr(), P * P, L.nq_dtype(self.sdtype))

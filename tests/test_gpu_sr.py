@@ -423,3 +423,40 @@ def test_streaming_sr_assembly(nq, ctx, dtype, P, Ns, real_params, chunks):
     rS, _ = OSR.sr_setup(rOc, np.zeros(P, np.complex128), real_params)
     H.assert_close(S.cpu().numpy().T, rS, tol, "streamed S")
     H.assert_close(sumO.cpu().numpy()[:P], O64.mean(axis=1), 1e-13, "<O>")
+
+
+@pytest.mark.parametrize("dtype,P,Ns,real_params", [(np.complex128, 230, 4200, False), (np.complex128, 300, 4500, True),
+                                                    (np.float64, 130, 4100, True), (np.complex128, 90, 1000, False)])
+def test_deferred_centring(nq, ctx, dtype, P, Ns, real_params):
+    """nq_center_lazy returns <O> and may leave O uncentred; the S assembly then subtracts the means on the fly (same S as
+    centre + setup), repeated setups keep working, and nq_center_finish produces the centred rows."""
+    L = nq._lib
+    rng = np.random.default_rng(31)
+    dtype = np.dtype(dtype)
+    O = (_rand(rng, (P, Ns), dtype) + dtype.type(0.7)).astype(dtype)
+    O64 = O.astype(np.complex128 if dtype.kind == "c" else np.float64)
+    d = _dev(O)
+    avg = np.zeros(P, dtype)
+    flag = L.C.c_int(-1)
+    L.check(L.lib.nq_center_lazy(ctx.h, d.data_ptr(), P, P, Ns, L.nq_dtype(dtype), L.ptr(avg), L.C.byref(flag)), ctx.h)
+    ravg, rOc = OSR.center(O64)
+    H.assert_close(avg, ravg, 1e-13, "<O>")
+    assert flag.value == (1 if Ns >= 4096 else 0)
+    if flag.value:
+        assert np.array_equal(d.cpu().numpy().T, O)              # untouched
+    sdt = np.dtype(dtype if (dtype.kind == "c" and not real_params) else np.float64)
+    g = np.ones(P, np.complex128)
+    rS, _ = OSR.sr_setup(rOc, g, real_params)
+    for rep in range(2):                                          # the second call finds no row maxima left behind
+        S = np.zeros((P, P), sdt, order="F")
+        F = np.zeros(P, sdt)
+        L.check(L.lib.nq_sr_setup(ctx.h, d.data_ptr(), P, P, Ns, Ns, L.nq_dtype(dtype), L.ptr(g), int(real_params), L.ptr(S), L.ptr(F)), ctx.h)
+        H.assert_close(S, rS, 1e-11, "S, deferred centring, call %d" % rep)
+    L.check(L.lib.nq_center_finish(ctx.h, d.data_ptr(), P, P, Ns, L.nq_dtype(dtype)), ctx.h)
+    assert np.max(np.abs(d.cpu().numpy().T - rOc)) <= 4e-11 * np.abs(O64).max()
+    L.check(L.lib.nq_center_finish(ctx.h, d.data_ptr(), P, P, Ns, L.nq_dtype(dtype)), ctx.h)      # nothing pending: no-op
+    assert np.max(np.abs(d.cpu().numpy().T - rOc)) <= 4e-11 * np.abs(O64).max()
+    S = np.zeros((P, P), sdt, order="F")
+    F = np.zeros(P, sdt)
+    L.check(L.lib.nq_sr_setup(ctx.h, d.data_ptr(), P, P, Ns, Ns, L.nq_dtype(dtype), L.ptr(g), int(real_params), L.ptr(S), L.ptr(F)), ctx.h)
+    H.assert_close(S, rS, 1e-11, "S after the explicit centring")
