@@ -186,12 +186,14 @@ class ClockSampler:
         return out
 
 
-def multi_gpu_parity(nq, torch, dist, ctx, net, liouv, world, rank, local, n_sub=4096):
-    """Cross-rank check of the exchange steps on a 4096-sample subset of the workload: the sharded iteration
+def multi_gpu_parity(nq, torch, dist, ctx, net, liouv, world, rank, local, n_sub=None):
+    """Cross-rank check of the exchange steps on a subset of the workload with 4096 samples PER RANK (so that every rank runs
+    the production path of the iteration: deferred centring + the integer-tensor-core S assembly): the sharded iteration
     (all-reduced <O>, F, S; replicated solve) against a SINGLE-RANK recomputation of the same samples on rank 0 (second
     context without a communicator), and bit-equality of the update across ranks.  ref: Parallel/MPI/mpi.jl:21-74."""
     w = WORKLOAD
     N, Lc = w["N"], w["L"]
+    n_sub = 4096 * world if n_sub is None else n_sub
     Bt = n_sub // Lc
     Bt -= Bt % world
     rng = np.random.Generator(np.random.Philox(777))          # same subset on every rank
