@@ -111,11 +111,12 @@ __global__ void oz_activity_kernel(const double* __restrict__ Xr, int64_t ldr, i
 }
 
 // ---- pre-pass 2: digits.  out[p][c][k][s] (int8, s contiguous; k padded to Ppad, s to Nspad with zeros), ex[k] = e_k + 1
-template <int NC>
+template <int NC, bool SHIFT>
 __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict__ Xr, int64_t ldr, int64_t P, int64_t Ns, int64_t Ppad,
                                                        int64_t Nspad, const unsigned long long* __restrict__ mx,
                                                        const double* __restrict__ shift /* (re, im) per row or NULL */,
-                                                       signed char* __restrict__ out, int* __restrict__ ex, int neg_plane) {
+                                                       signed char* __restrict__ out, int* __restrict__ ex, int neg_plane,
+                                                       const unsigned* __restrict__ tflags /* NC = 2: live planes per 128 rows */) {
     extern __shared__ signed char tile[];                 // [NSL][32 NC][128 + 4]
     constexpr int ROWS = 32 * NC, LD = 128 + 4;
     const int tid = threadIdx.x;
@@ -127,10 +128,10 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
     const int64_t k = k0 + rr / NC;
     int e = 0;
     // deferred centring: the values are x - shift; mx then bounds the UNcentred row, |shift| is added to the bound
-    const double sh = (shift && k < P) ? shift[2 * k + (NC == 2 ? rr % NC : 0)] : 0.0;
+    const double sh = (SHIFT && k < P) ? shift[2 * k + (NC == 2 ? rr % NC : 0)] : 0.0;
     if (k < P) {
         double m = __longlong_as_double((long long)mx[k]);
-        if (shift) m += fmax(fabs(shift[2 * k]), fabs(shift[2 * k + 1]));
+        if (SHIFT) m += fmax(fabs(shift[2 * k]), fabs(shift[2 * k + 1]));
         if (m > 0.0) { frexp(m, &e); }                     // m = f 2^e, f in [0.5, 1)
         e += 1;                                            // |x| 2^-e <= 0.5: every digit fits [-64, 64]
         if (rr % NC == 0 && blockIdx.x == 0 && sl0 == 0) ex[k] = e;
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
         ex[k] = 0;
     }
     const double sc49 = scalbn(1.0, 7 * NSL - e);          // x 2^-e in (-1/2, 1/2), times 2^49
+    const double msh49 = -sh * sc49;
     // a task = 4 consecutive samples of one row: four loads (each coalesced over the 32 rows of the warp), 4 x 7 digits, packed
     // into one 32-bit word per slice (byte stores cost four times the shared-memory instructions)
     for (int j0 = sl0; j0 < 32; j0 += 2 * SLN) {            // two tasks (8 loads) in flight per thread
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
             for (int w = 0; w < 4; w++) {
                 const int j = j0 + u * SLN;
                 const int64_t smp = s0 + 4 * j + w;
-                yv[u][w] = (k < P && j < 32 && smp < Ns) ? Xr[(k0 * NC + rr) + ldr * smp] - sh : 0.0;
+                yv[u][w] = (k < P && j < 32 && smp < Ns) ? Xr[(k0 * NC + rr) + ldr * smp] : sh;      // raw value; sh -> digit 0
             }
 #pragma unroll
         for (int u = 0; u < 2; u++) {
@@ -160,7 +162,10 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
 #pragma unroll
             for (int w = 0; w < 4; w++) {
                 // y 2^49 as a 64-bit integer (|y| < 1/2: 48 bits), then 7 balanced base-128 digits, least significant first
-                long long v = __double2ll_rn(yv[u][w] * sc49);
+                // (x - sh) 2^(49-e): the power of two commutes with the rounding of x - sh, so one fma gives the bits of
+                // (x - sh) * sc49 and the eight loads of the task pair stay in flight (a subtraction after each load made ptxas
+                // recycle the load registers: 1.16 -> 1.81 ms)
+                long long v = __double2ll_rn(SHIFT ? fma(yv[u][w], sc49, msh49) : yv[u][w] * sc49);
 #pragma unroll
                 for (int p = NSL - 1; p >= 1; p--) {
                     const int q = (int)((v + 64) & 127) - 64;
@@ -180,8 +185,18 @@ __global__ void __launch_bounds__(256) oz_split_kernel(const double* __restrict_
     // A_re B_im^T - A_im B_re^T and the integer MMA has no negate flag
     const size_t plane = (size_t)Ppad * Nspad;
     const int NP = NC + neg_plane;
-    for (int line = warp; line < NSL * ROWS; line += 8) {
-        const int p = line / ROWS, r2 = line % ROWS, c = r2 % NC, kk = r2 / NC;
+    // a component plane that is zero over the whole 128-row tile is never loaded by the product kernel (same flags): its
+    // digits are not written (NDM gradients: every column is purely real or purely imaginary -- half of the planes)
+    const unsigned live = (NC == 2 && tflags) ? (tflags[k0 / 128] & 3u) : (NC == 2 ? 3u : 1u);
+    const int ncl = NC == 2 ? __popc(live) : 1;            // live components of this tile: the 8 warps share their lines
+    // shifts, not divisions (a runtime divisor doubled the kernel's instruction count: 1.2 -> 1.8 ms).  The order matters: the 8
+    // warps write 8 consecutive lines of one slice per step; giving each warp its 8 rows back to back (strength-reduced
+    // pointers, unrolled) was 35 % SLOWER -- the write-back order of L2 follows the store order
+    const int lsh = ncl == 2 ? 6 : 5, csh = ncl == 2 ? 1 : 0;
+    for (int line = warp; line < (NSL << lsh); line += 8) {
+        const int p = line >> lsh, rem = line & ((1 << lsh) - 1), kk = rem >> csh;
+        const int c = ncl == NC ? (rem & (NC - 1)) : (int)(live >> 1);   // one live component: 0 (flags 01) or 1 (flags 10)
+        const int r2 = kk * NC + c;
         const int word = *reinterpret_cast<const int*>(&tile[(p * ROWS + r2) * LD + 4 * lane]);
         const size_t at = (size_t)(k0 + kk) * Nspad + s0 + 4 * lane;
         *reinterpret_cast<int*>(out + ((size_t)(p * NP + c)) * plane + at) = word;
@@ -570,9 +585,11 @@ int run_ozaki(nq_ctx_t ctx, const double* X, int64_t ldr, int64_t P, int64_t Ns,
     {
         dim3 g((unsigned)(Nspad / 128), (unsigned)(Ppad / 32));
         const size_t smem = (size_t)NSL * 32 * NC * (128 + 4);
-        auto ks = oz_split_kernel<NC>;
+        auto ks = shift ? oz_split_kernel<NC, true> : oz_split_kernel<NC, false>;
+        static const bool skip_dead = [] { const char* e = getenv("NQ_OZ_SKIP"); return !(e && e[0] == '0'); }();
         NQ_CUDA(ctx, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NQ_LAUNCH(ctx, ks, g, 256, smem, X, ldr, P, Ns, Ppad, Nspad, (const unsigned long long*)mx, shift, ops, ex, neg_plane);
+        NQ_LAUNCH(ctx, ks, g, 256, smem, X, ldr, P, Ns, Ppad, Nspad, (const unsigned long long*)mx, shift, ops, ex, neg_plane,
+                  skip_dead ? (const unsigned*)flags : (const unsigned*)nullptr);
     }
     CUtensorMap mapA, mapB;
     {
