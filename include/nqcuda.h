@@ -174,6 +174,14 @@ int nq_local_grad(nq_machine_t m, nq_operator_t op, const void* srow, const void
 int nq_logpsi_grad_local_packed(nq_machine_t m, nq_operator_t op, const uint64_t* prow, const uint64_t* pcol,
                                 int64_t B, void* out_logpsi, void* O, int64_t ldO, void* out_loc, void* out_gloc,
                                 int64_t ld);
+/* the same step for configurations held by the HOST (srow / scol [N,B] float arrays, pinned memory makes the copies
+ * asynchronous): copy + packing of piece c+1 run on a side stream of the context while the fused kernel works on piece c
+ * (pieces of 2 rounds, 7 rounds, the rest of the persistent kernel); prow / pcol [W64,B] (device) receive the packed words,
+ * all outputs are device buffers as above.  Results are bit-identical to nq_pack_states + nq_logpsi_grad_local_packed.
+ * ref: BatchedGradSampler.jl:83-97 (sample, then evaluate the batch), Samplers/Metropolis.jl:124-167 (host float states) */
+int nq_logpsi_grad_local_host(nq_machine_t m, nq_operator_t op, const void* srow, const void* scol, nq_dtype sdtype,
+                              int64_t B, uint64_t* prow, uint64_t* pcol, void* out_logpsi, void* O, int64_t ldO,
+                              void* out_loc, void* out_gloc, int64_t ld);
 int nq_local_scalar_packed(nq_machine_t m, nq_operator_t op, const uint64_t* prow, const uint64_t* pcol,
                            int64_t B, void* out_loc);
 int nq_local_grad_packed(nq_machine_t m, nq_operator_t op, const uint64_t* prow, const uint64_t* pcol,

@@ -540,4 +540,17 @@ nesterov!(ctx::Ctx, delta, velocity, Δ, n::Integer, T::Type, o) =
     check(ctx, ccall((:nq_nesterov, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Cdouble, Cdouble, Ptr{Cvoid}),
                      ctx.h, velocity, Δ, n, nqdtype(T), o.lr, o.μ, delta))
 
+# One iteration step from HOST configurations (σ, σ′ as the reference's sampler holds them, [N, Ns] floats): copy, packing and the
+# fused kernel software-pipelined inside the library.  prow / pcol / logρ / O / L_loc / ∇L_loc are device pointers (CuPtr or
+# Ptr from the caller's allocator); replaces the two loops of sample!(is::BatchedGradSampler) (BatchedGradSampler.jl:80-97).
+function logpsi_grad_local_host!(c::CudaNet, op::CudaOperator, σr::Matrix{T}, σc::Union{Matrix{T},Nothing},
+                                 prow, pcol, logρ, O, ldO::Integer, Lloc, ∇Lloc, ld::Integer) where {T<:AbstractFloat}
+    Ns = size(σr, 2)
+    GC.@preserve σr σc check(c.ctx, ccall((:nq_logpsi_grad_local_host, lib), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64,
+         Ptr{Cvoid}, Ptr{Cvoid}, Int64),
+        c.h, op.h, pointer(σr), σc === nothing ? C_NULL : pointer(σc), nqdtype(T), Ns, prow, pcol === nothing ? C_NULL : pcol,
+        logρ, O, ldO, Lloc, ∇Lloc === nothing ? C_NULL : ∇Lloc, ld))
+end
+
 end # module

@@ -48,6 +48,9 @@ struct nq_ctx_s {
     bool shift_pending = false;            // stays set until the subtraction happened (nq_center_finish, an S path that centres
     const void* shift_ptr = nullptr;       // in place) or the matrix is re-centred / rewritten by a machine kernel
     int64_t shift_P = 0, shift_Ns = 0, shift_ld = 0;
+    // side stream + events of the software-pipelined host entry (nq_logpsi_grad_local_host), created on first use
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t side_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool shift_matches(const void* X, int64_t ld, int64_t P, int64_t Ns) const {
         return shift_pending && shift_ptr == X && shift_P == P && shift_Ns == Ns && shift_ld == ld;
     }

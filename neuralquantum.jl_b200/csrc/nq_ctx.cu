@@ -86,6 +86,8 @@ extern "C" int nq_ctx_destroy(nq_ctx_t ctx) {
     for (auto& s : ctx->slots) if (s.p) cudaFree(s.p);
     if (ctx->rowmax) cudaFree(ctx->rowmax);
     if (ctx->shift) cudaFree(ctx->shift);
+    for (auto& e : ctx->side_ev) if (e) cudaEventDestroy(e);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return NQ_OK;

@@ -521,6 +521,66 @@ extern "C" int nq_logpsi_grad_local_packed(nq_machine_t m, nq_operator_t op, con
     return nq_local_device(m, op, prow, pcol, B, out_logpsi, O, ldO, out_loc, out_gloc, ld);
 }
 
+// The same step for configurations held by the HOST as float arrays (what the reference's sampler hands over), software
+// pipelined inside the library: the batch is cut into pieces that grow in units of one ROUND of the persistent kernel (one
+// configuration per resident warp: 2 rounds, 7 rounds, the rest); the float arrays of piece c+1 are copied and packed on a
+// side stream while the fused kernel works on piece c, so only the copy of the first piece is exposed (a piece copies ~3.6x
+// faster than it computes) and whole rounds keep the total number of rounds.  prow / pcol receive the packed words.
+// ref: BatchedGradSampler.jl:83-97 (the reference copies nothing: its arrays live where they are computed)
+extern "C" int nq_logpsi_grad_local_host(nq_machine_t m, nq_operator_t op, const void* srow, const void* scol, nq_dtype sdtype,
+                                         int64_t B, uint64_t* prow, uint64_t* pcol, void* out_logpsi, void* O, int64_t ldO,
+                                         void* out_loc, void* out_gloc, int64_t ld) {
+    if (!m || !op || !srow || !prow || !out_logpsi || !O || !out_loc || B < 0) return NQ_ERR_ARG;
+    nq_ctx_t ctx = m->ctx;
+    if (m->doubled() != (scol != nullptr) || m->doubled() != (pcol != nullptr)) return nq_fail(ctx, NQ_ERR_ARG, "row/col configuration mismatch");
+    if (ldO < m->P || (out_gloc && ld < m->P)) return nq_fail(ctx, NQ_ERR_SHAPE, "leading dimension < P");
+    if (out_gloc && op->space != NQ_SUPER) return nq_fail(ctx, NQ_ERR_UNSUPPORTED, "gradient estimator is defined for Liouvillians only");
+    if (sdtype != NQ_F32 && sdtype != NQ_F64) return nq_fail(ctx, NQ_ERR_ARG, "state arrays must be NQ_F32 or NQ_F64");
+    NQ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (nq_is_device_ptr(srow) || (scol && nq_is_device_ptr(scol)))
+        return nq_fail(ctx, NQ_ERR_ARG, "nq_logpsi_grad_local_host takes HOST configurations (device arrays: nq_pack_states + the packed entry)");
+    if (!nq_is_device_ptr(prow) || (pcol && !nq_is_device_ptr(pcol)) || !nq_is_device_ptr(O) || !nq_is_device_ptr(out_logpsi) ||
+        !nq_is_device_ptr(out_loc) || (out_gloc && !nq_is_device_ptr(out_gloc)))
+        return nq_fail(ctx, NQ_ERR_ARG, "the outputs of the fused entry point are device-resident buffers");
+    if (B == 0) return NQ_OK;
+    const int N = m->N, W = nq_words(N);
+    const size_t fs = nq_dtype_size(sdtype), es = nq_dtype_size(m->out_dtype), cs = nq_dtype_size(nq_complex_of(m->dtype));
+    char* stage_r = (char*)nq_scratch(ctx, SL_IN0, (size_t)B * N * fs);
+    char* stage_c = scol ? (char*)nq_scratch(ctx, SL_IN1, (size_t)B * N * fs) : nullptr;
+    if (!stage_r || (scol && !stage_c)) return NQ_ERR_ALLOC;
+    if (!ctx->side_stream) {
+        NQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+        for (auto& e : ctx->side_ev) NQ_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const int64_t rnd = (int64_t)ctx->num_sms * 16;
+    int64_t bounds[4] = {0, B, B, B};
+    int npiece = 1;
+    if (B >= 16 * rnd) { bounds[1] = 2 * rnd; bounds[2] = 9 * rnd; bounds[3] = B; npiece = 3; }
+    else if (B >= 6 * rnd) { bounds[1] = 2 * rnd; bounds[2] = B; npiece = 2; }
+    ctx->shift_pending = false; ctx->rowmax_ptr = nullptr;          // new rows: records of a centring pass are stale
+    cudaStream_t main_stream = ctx->stream, side = ctx->side_stream;
+    // the staging and packed buffers may still be read by earlier work on the main stream
+    NQ_CUDA(ctx, cudaEventRecord(ctx->side_ev[3], main_stream));
+    NQ_CUDA(ctx, cudaStreamWaitEvent(side, ctx->side_ev[3], 0));
+    for (int c = 0; c < npiece; c++) {
+        const int64_t c0 = bounds[c], n = bounds[c + 1] - bounds[c];
+        const size_t foff = (size_t)c0 * N * fs;
+        NQ_CUDA(ctx, cudaMemcpyAsync(stage_r + foff, (const char*)srow + foff, (size_t)n * N * fs, cudaMemcpyHostToDevice, side));
+        if (scol) NQ_CUDA(ctx, cudaMemcpyAsync(stage_c + foff, (const char*)scol + foff, (size_t)n * N * fs, cudaMemcpyHostToDevice, side));
+        ctx->stream = side;                                         // the packing kernels follow their copies
+        int rc = nq_pack_device(ctx, m->hilb, N, n, stage_r + foff, sdtype, prow + c0 * W);
+        if (rc == NQ_OK && scol) rc = nq_pack_device(ctx, m->hilb, N, n, stage_c + foff, sdtype, pcol + c0 * W);
+        ctx->stream = main_stream;
+        if (rc != NQ_OK) return rc;
+        NQ_CUDA(ctx, cudaEventRecord(ctx->side_ev[c], side));
+        NQ_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->side_ev[c], 0));
+        NQ_CHECK(nq_local_device(m, op, prow + c0 * W, pcol ? pcol + c0 * W : nullptr, n, (char*)out_logpsi + (size_t)c0 * es,
+                                 (char*)O + (size_t)c0 * ldO * es, ldO, (char*)out_loc + (size_t)c0 * cs,
+                                 out_gloc ? (char*)out_gloc + (size_t)c0 * ld * cs : nullptr, ld));
+    }
+    return NQ_OK;
+}
+
 #ifdef NQ_PROFILE_PHASES
 extern "C" int nq_debug_phase_cycles(unsigned long long out[8], int reset) {
     cudaDeviceSynchronize();

@@ -93,6 +93,7 @@ _PROTOS = {
     "nq_local_scalar": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "nq_local_grad": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _i64]),
     "nq_logpsi_grad_local_packed": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64]),
+    "nq_logpsi_grad_local_host": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64]),
     "nq_local_scalar_packed": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "nq_local_grad_packed": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64]),
     "nq_sampler_create": (_i32, [_vp, _i64, _i32, _u64, _i64, C.POINTER(_vp)]),

@@ -151,16 +151,38 @@ class BatchedSampler:
         L.check(L.lib.nq_logpsi_grad_local_packed(net.h, self.op.h, self.prow.data_ptr(), pc, Ns, self.logpsi.data_ptr(),
                                                   self._O.data_ptr(), net.P, self.loc.data_ptr(), gl, net.P), ctx.h)
 
-    def evaluate_host(self, sigma, chunks=2):
+    def evaluate_host(self, sigma, chunks=None):
         """set_samples + evaluate for HOST configurations [N, B, L] (pinned memory makes the copies asynchronous), software
-        pipelined: the batch is cut into `chunks` pieces; the float arrays of piece c+1 are copied on a side stream while the
+        pipelined: the batch is cut into pieces; the float arrays of piece c+1 are copied on a side stream while the
         fused kernel works on piece c (the kernel is persistent and fills every SM, so only the copy engine overlaps; the
         two small packing kernels of a piece run between two fused launches).  Same results as set_samples(sigma);
-        evaluate() -- every copy still happens inside the call."""
+        evaluate() -- every copy still happens inside the call.
+
+        chunks = None (default): ONE library call, nq_logpsi_grad_local_host -- the pipeline runs inside libnqcuda on a growing
+        schedule in units of one ROUND of the persistent kernel (one configuration per resident warp): 2 rounds, 7 rounds,
+        the rest.  Only the copy of the first piece is exposed, a piece copies ~3.6x faster than it computes so every later
+        copy hides behind the piece before it, and whole rounds keep the total number of rounds of the launch.
+        chunks = k: k equal pieces, pipelined from this mirror with torch streams (kept for comparison)."""
         from .core import Context
         torch = _torch()
         net, ctx, Ns, P = self.net, self.ctx, self.Ns, self.net.P
-        if self.symm or chunks <= 1 or Ns < 8192 * chunks:      # measured: 8192 samples per GPU are faster in one piece
+        if self.symm:
+            self.set_samples(sigma)
+            return self.evaluate()
+        if chunks is None:
+            sr, sc = sigma if net.doubled else (sigma, None)
+            hs = [np.asfortranarray(a).reshape(net.N, Ns, order="F") for a in (sr, sc) if a is not None]
+            if hs[0].dtype not in (np.float32, np.float64) or any(h.dtype != hs[0].dtype for h in hs):
+                hs = [np.asfortranarray(h, dtype=np.float64) for h in hs]
+            self._center_pending = False
+            gl = self.gloc.data_ptr() if self.is_liouvillian else None
+            L.check(L.lib.nq_logpsi_grad_local_host(net.h, self.op.h, hs[0].ctypes.data, hs[1].ctypes.data if len(hs) > 1 else None,
+                                                    L.nq_dtype(hs[0].dtype), Ns, self.prow.data_ptr(),
+                                                    self.pcol.data_ptr() if self.pcol is not None else None,
+                                                    self.logpsi.data_ptr(), self._O.data_ptr(), P, self.loc.data_ptr(), gl, P), ctx.h)
+            return
+        bounds = [0, Ns] if (chunks <= 1 or Ns < 8192 * chunks) else [(Ns * c) // chunks for c in range(chunks + 1)]
+        if len(bounds) == 2:                   # measured: 8192 samples per GPU are faster in one piece
             self.set_samples(sigma)
             return self.evaluate()
         dev = torch.device("cuda", ctx.device)
@@ -176,9 +198,8 @@ class BatchedSampler:
         es, cs = self._O.element_size(), self.loc.element_size()
         self._center_pending = False
         fcode = L.nq_dtype(np.dtype(str(hosts[0].dtype).replace("torch.", "")))
-        bounds = [(Ns * c) // chunks for c in range(chunks + 1)]
         side_stream.wait_stream(main_stream)                       # the staging / packed buffers may still be read by earlier work
-        for c in range(chunks):
+        for c in range(len(bounds) - 1):
             c0, n = bounds[c], bounds[c + 1] - bounds[c]
             with torch.cuda.stream(side_stream):
                 for i, h in enumerate(hosts):

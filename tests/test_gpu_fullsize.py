@@ -134,7 +134,7 @@ def test_pipelined_host_evaluate_is_bit_identical(nq, ctx):
     """BatchedSampler.evaluate_host (copies and packing of piece c+1 on a side stream while the fused kernel works on piece c)
     gives exactly the arrays of set_samples + evaluate."""
     import torch
-    N, B, Lc = 8, 2048, 8
+    N, B, Lc = 8, 4096, 10                         # 40 960 configurations = 17.3 rounds of 148 x 16 warps: three pieces by default
     om, pm, hilb = H.make_pair(nq, ctx, "ndm", "fock", N, 2, np.float64, 0, seed=4, std=0.2)
     _, _, _, pl = H.p_lindblad_ising_1d(nq, N)
     bs = nq.BatchedSampler(pm, nq.MetropolisSampler(nq.LocalRule(), Lc, N, burn=1, seed=1), pl, nq.SR(np.float32, eps=0.001), batch_sz=B)
@@ -148,7 +148,10 @@ def test_pipelined_host_evaluate_is_bit_identical(nq, ctx):
     ref = [t.clone() for t in (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc)]
     for t in (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc):
         t.zero_()
-    bs.evaluate_host(sig, chunks=2)
-    torch.cuda.synchronize()
-    for a, b in zip(ref, (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc)):
-        assert torch.equal(a, b)
+    for chunks in (2, None):                       # equal pieces; the growing default schedule (2 rounds, 7 rounds, rest)
+        for t in (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc):
+            t.zero_()
+        bs.evaluate_host(sig, chunks=chunks)
+        torch.cuda.synchronize()
+        for a, b in zip(ref, (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc)):
+            assert torch.equal(a, b)
