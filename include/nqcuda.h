@@ -178,6 +178,8 @@ int nq_logpsi_grad_local_packed(nq_machine_t m, nq_operator_t op, const uint64_t
  * asynchronous): copy + packing of piece c+1 run on a side stream of the context while the fused kernel works on piece c
  * (pieces of 2 rounds, 7 rounds, the rest of the persistent kernel); prow / pcol [W64,B] (device) receive the packed words,
  * all outputs are device buffers as above.  Results are bit-identical to nq_pack_states + nq_logpsi_grad_local_packed.
+ * The call returns once everything is enqueued: with pinned arrays the last copies may still be in flight, so srow / scol
+ * must not be modified before the context's stream has been synchronised (nq_ctx_sync; the stream waits for every copy).
  * ref: BatchedGradSampler.jl:83-97 (sample, then evaluate the batch), Samplers/Metropolis.jl:124-167 (host float states) */
 int nq_logpsi_grad_local_host(nq_machine_t m, nq_operator_t op, const void* srow, const void* scol, nq_dtype sdtype,
                               int64_t B, uint64_t* prow, uint64_t* pcol, void* out_logpsi, void* O, int64_t ldO,

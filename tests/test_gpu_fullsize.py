@@ -148,7 +148,13 @@ def test_pipelined_host_evaluate_is_bit_identical(nq, ctx):
     ref = [t.clone() for t in (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc)]
     for t in (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc):
         t.zero_()
-    for chunks in (2, None):                       # equal pieces; the growing default schedule (2 rounds, 7 rounds, rest)
+    # the library entry takes HOST configurations only and says so (device arrays go through nq_pack_states + the packed entry)
+    L = nq._lib
+    with pytest.raises(nq.NQError):
+        L.check(L.lib.nq_logpsi_grad_local_host(pm.h, bs.op.h, bs.prow.data_ptr(), bs.pcol.data_ptr(), L.NQ_F64, Ns, bs.prow.data_ptr(),
+                                                bs.pcol.data_ptr(), bs.logpsi.data_ptr(), bs.O.data_ptr(), pm.P, bs.loc.data_ptr(),
+                                                bs.gloc.data_ptr(), pm.P), ctx.h)
+    for chunks in (2, None):                       # equal pieces from the mirror; the library's growing schedule (2 rounds, 7, rest)
         for t in (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc):
             t.zero_()
         bs.evaluate_host(sig, chunks=chunks)
