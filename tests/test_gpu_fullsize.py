@@ -161,3 +161,29 @@ def test_pipelined_host_evaluate_is_bit_identical(nq, ctx):
         torch.cuda.synchronize()
         for a, b in zip(ref, (bs.prow, bs.pcol, bs.logpsi, bs.O, bs.loc, bs.gloc)):
             assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.complex128, np.float32])
+def test_host_entry_ket_machine_is_bit_identical(nq, ctx, dtype):
+    """nq_logpsi_grad_local_host on a ket machine (RBM + Hamiltonian: no sigma', no gradient of the estimator; the library
+    runs its two kernels per piece) against set_samples + evaluate, float32 and float64 host arrays."""
+    import torch
+    N, B, Lc = 12, 2048, 8                         # 16 384 configurations: two pieces (2 rounds + the rest)
+    om, pm, hilb = H.make_pair(nq, ctx, "rbm", "spin", N, 2, dtype, OM.LOGCOSH, seed=7)
+    _, pH = H.p_tfim_1d(nq, N)
+    bs = nq.BatchedSampler(pm, nq.MetropolisSampler(nq.LocalRule(), Lc, N, burn=1, seed=1), pH, nq.SR(np.float32, eps=0.001), batch_sz=B)
+    Ns = B * Lc
+    for fdt in (np.float64, np.float32):
+        sig = np.asfortranarray(H.rand_states("spin", N, Ns, 21).astype(fdt)).reshape(N, B, Lc, order="F")
+        bs.set_samples(sig)
+        bs.evaluate()
+        torch.cuda.synchronize()
+        ref = [t.clone() for t in (bs.prow, bs.logpsi, bs.O, bs.loc)]
+        for t in (bs.prow, bs.logpsi, bs.O, bs.loc):
+            t.zero_()
+        bs.evaluate_host(sig)
+        torch.cuda.synchronize()
+        for a, b in zip(ref, (bs.prow, bs.logpsi, bs.O, bs.loc)):
+            assert torch.equal(a, b)
+        assert int((bs.loc != 0).sum()) > 0
