@@ -553,4 +553,118 @@ function logpsi_grad_local_host!(c::CudaNet, op::CudaOperator, œÉr::Matrix{T}, œ
         logœÅ, O, ldO, Lloc, ‚àáLloc === nothing ? C_NULL : ‚àáLloc, ld))
 end
 
+# ---- device-resident entry points and utilities (every remaining symbol of include/nqcuda.h) -------------------------
+# The iteration keeps its arrays on the device between the calls: configurations as bit-packed words (what the sampler
+# leaves behind), log œÅ / O / L_loc / ‚àáL_loc in the caller's device buffers.  `DevPtr` is whatever the caller's allocator
+# hands out (CUDA.jl: `pointer(::CuArray)` reinterpreted to Ptr{Cvoid}).
+const DevPtr = Ptr{Cvoid}
+version() = ccall((:nq_version, lib), Cint, ())
+status_string(st::Integer) = unsafe_string(ccall((:nq_status_string, lib), Cstring, (Cint,), st))
+sync(ctx::Ctx) = check(ctx, ccall((:nq_ctx_sync, lib), Cint, (Ptr{Cvoid},), ctx.h))
+function launch_count(ctx::Ctx)
+    n = Ref{UInt64}(0)
+    check(ctx, ccall((:nq_ctx_launch_count, lib), Cint, (Ptr{Cvoid}, Ptr{UInt64}), ctx.h, n))
+    return n[]
+end
+states_words(N::Integer) = ccall((:nq_states_words, lib), Cint, (Cint,), N)
+"œÉ [N, B] floats (host or device) ‚Üí packed words [W64, B] on the device (States.jl:12-32 ‚Üî HomogeneousSpin.jl:156-179)."
+pack_states!(packed::DevPtr, ctx::Ctx, hilb, œÉ::AbstractMatrix{T}) where {T} =
+    GC.@preserve œÉ check(ctx, ccall((:nq_pack_states, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                                    ctx.h, hilbcode(hilb), size(œÉ, 1), size(œÉ, 2), pointer(œÉ), nqdtype(T), packed))
+unpack_states!(œÉ::AbstractMatrix{T}, ctx::Ctx, hilb, packed::DevPtr) where {T} =
+    GC.@preserve œÉ check(ctx, ccall((:nq_unpack_states, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                                    ctx.h, hilbcode(hilb), size(œÉ, 1), size(œÉ, 2), packed, pointer(œÉ), nqdtype(T)))
+function nparams(c::CudaNet)
+    P = Ref{Int64}(0)
+    check(c.ctx, ccall((:nq_machine_nparams, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}), c.h, P))
+    return Int(P[])
+end
+function out_dtype(c::CudaNet)                                        # out_type(net)
+    d = Ref{Cint}(0)
+    check(c.ctx, ccall((:nq_machine_out_dtype, lib), Cint, (Ptr{Cvoid}, Ptr{Cint}), c.h, d))
+    return d[]
+end
+function nparams(g::CudaSymm)
+    P = Ref{Int64}(0)
+    check(g.ctx, ccall((:nq_symm_nparams, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}), g.h, P))
+    return Int(P[])
+end
+"logœà! / logœà_and_‚àálogœà! on packed device configurations (no conversion pass)."
+logpsi_packed!(out::DevPtr, c::CudaNet, prow::DevPtr, pcol::DevPtr, B::Integer) =
+    check(c.ctx, ccall((:nq_logpsi_packed, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}), c.h, prow, pcol, B, out))
+logpsi_grad_packed!(out::DevPtr, O::DevPtr, ldO::Integer, c::CudaNet, prow::DevPtr, pcol::DevPtr, B::Integer) =
+    check(c.ctx, ccall((:nq_logpsi_grad_packed, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Int64),
+                       c.h, prow, pcol, B, out, O, ldO))
+"The fused iteration step on the samples the sampler left on the device (BatchedGradSampler.jl:83-97 / BatchedValSampler.jl:122-125)."
+logpsi_grad_local_packed!(logœà::DevPtr, O::DevPtr, ldO::Integer, Lloc::DevPtr, ‚àáLloc::DevPtr, ld::Integer, c::CudaNet,
+                          op::CudaOperator, prow::DevPtr, pcol::DevPtr, B::Integer) =
+    check(c.ctx, ccall((:nq_logpsi_grad_local_packed, lib), Cint,
+                       (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Int64),
+                       c.h, op.h, prow, pcol, B, logœà, O, ldO, Lloc, ‚àáLloc, ld))
+local_scalar_packed!(Lloc::DevPtr, c::CudaNet, op::CudaOperator, prow::DevPtr, pcol::DevPtr, B::Integer) =
+    check(c.ctx, ccall((:nq_local_scalar_packed, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}),
+                       c.h, op.h, prow, pcol, B, Lloc))
+local_grad_packed!(Lloc::DevPtr, ‚àáLloc::DevPtr, ld::Integer, c::CudaNet, op::CudaOperator, prow::DevPtr, pcol::DevPtr, B::Integer) =
+    check(c.ctx, ccall((:nq_local_grad_packed, lib), Cint,
+                       (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Int64),
+                       c.h, op.h, prow, pcol, B, Lloc, ‚àáLloc, ld))
+function max_connections(op::CudaOperator)
+    n = Ref{Int64}(0)
+    check(op.ctx, ccall((:nq_operator_max_connections, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}), op.h, n))
+    return Int(n[])
+end
+"""
+row_valdiff! over a batch (BaseOperators.jl:25-36, KLocalOperator.jl:151-159): per configuration the ordered connection list
+of the reference -- counts [B], matrix elements [max_conn, B], flip masks [W64, max_conn, B] (integer-parity artefacts).
+"""
+function connections(op::CudaOperator, hilb, œÉr::Matrix{T}, œÉc::Union{Matrix{T},Nothing} = nothing) where {T}
+    N, B = size(œÉr); mc = max_connections(op); W = Int(states_words(N))
+    counts = zeros(Int32, B); mels = zeros(ComplexF64, mc, B)
+    fr = zeros(UInt64, W, mc, B); fc = œÉc === nothing ? nothing : zeros(UInt64, W, mc, B)
+    GC.@preserve œÉr œÉc counts mels fr fc check(op.ctx, ccall((:nq_connections, lib), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Int32}, Ptr{Cvoid}, Ptr{UInt64}, Ptr{UInt64}),
+        op.h, hilbcode(hilb), pointer(œÉr), œÉc === nothing ? C_NULL : pointer(œÉc), nqdtype(T), B, mc, counts, mels, fr,
+        fc === nothing ? C_NULL : pointer(fc)))
+    return counts, mels, fr, fc
+end
+"Chain state in and out (parity tests; Metropolis.jl:101-115 writes it with rand!)."
+set_state!(sc::CudaSamplerCache, œÉr::Matrix{T}, œÉc = nothing) where {T} =
+    GC.@preserve œÉr œÉc check(sc.ctx, ccall((:nq_sampler_set_state, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                                           sc.h, pointer(œÉr), œÉc === nothing ? C_NULL : pointer(œÉc), nqdtype(T)))
+get_state!(œÉr::Matrix{T}, œÉc, sc::CudaSamplerCache) where {T} =
+    GC.@preserve œÉr œÉc check(sc.ctx, ccall((:nq_sampler_get_state, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                                           sc.h, pointer(œÉr), œÉc === nothing ? C_NULL : pointer(œÉc), nqdtype(T)))
+"diagonal = true: the chain of the observables sampler over œÅ(œÉ, œÉ) (BatchedObsDMSampler.jl:59-105)."
+set_mode!(sc::CudaSamplerCache, diagonal::Bool) =
+    check(sc.ctx, ccall((:nq_sampler_set_mode, lib), Cint, (Ptr{Cvoid}, Cint), sc.h, diagonal ? 1 : 0))
+"stat_analysis (utils/stats.jl:26-84) of [B, L] values on the device: (mean, error, variance, œÑ, RÃÇ), global under sharding."
+function stat_analysis(ctx::Ctx, vals::DevPtr, B::Integer, L::Integer, T::Type)
+    out = zeros(Float64, 6)
+    check(ctx, ccall((:nq_stat_analysis, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Cint, Ptr{Float64}), ctx.h, vals, B, L, nqdtype(T), out))
+    return (mean = complex(out[1], out[2]), error = out[3], variance = out[4], tau = out[5], R = out[6])
+end
+"Matrix-free CG on the centred rows (SR_notfull.jl:47-148, SRIterative.jl:117-132): the plain-CG form of _solve! without an explicit S."
+function solve_matfree_cg!(Œîw::Vector, ctx::Ctx, Oc::AbstractMatrix, Ns_total::Integer, F::Vector, real_params::Bool,
+                           œµ::Float64, tol::Float64, maxiter::Integer = 0)
+    its = Ref{Int64}(0)
+    P = size(Oc, 1)
+    GC.@preserve Œîw Oc F check(ctx, ccall((:nq_sr_solve_matfree, lib), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Cint, Ptr{Cvoid}, Cint, Cdouble, Cdouble, Int64, Ptr{Cvoid}, Ptr{Int64}),
+        ctx.h, pointer(Oc), P, P, size(Oc, 2), Ns_total, nqdtype(Oc), pointer(F), real_params ? 1 : 0, œµ, tol, maxiter,
+        pointer(Œîw), its))
+    return Œîw, Int(its[])
+end
+"abs2.(local_vals) (BatchedGradSampler.jl:99) on the device."
+abs2!(out::DevPtr, ctx::Ctx, vals::DevPtr, n::Integer, T::Type) =
+    check(ctx, ccall((:nq_abs2, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Ptr{Cvoid}), ctx.h, vals, n, nqdtype(T), out))
+function comm_size(ctx::Ctx)                                          # num_workers / worker rank (mpi.jl:36-51)
+    n, r = Ref{Cint}(1), Ref{Cint}(0)
+    check(ctx, ccall((:nq_comm_size, lib), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}), ctx.h, n, r))
+    return Int(n[]), Int(r[])
+end
+comm_destroy!(ctx::Ctx) = check(ctx, ccall((:nq_comm_destroy, lib), Cint, (Ptr{Cvoid},), ctx.h))
+"Uneven shards (Metropolis.jl:75 shards the chain length with ceil): the global sample count the normalisations use."
+set_global_samples!(ctx::Ctx, ns_total::Integer) =
+    check(ctx, ccall((:nq_comm_set_global_samples, lib), Cint, (Ptr{Cvoid}, Int64), ctx.h, ns_total))
+
 end # module

@@ -25,6 +25,19 @@ def test_library_exports_every_declared_symbol(nq):
     assert lib.nq_version() == 100
 
 
+def test_reference_side_bindings_cover_the_header():
+    """Every entry point the header declares is bound in the Julia shim (a `ccall((:name, lib), ...)`) and mapped to the
+    reference interface it replaces in INTEGRATION.md."""
+    hdr = open(os.path.join(ROOT, "include", "nqcuda.h")).read()
+    declared = sorted(set(re.findall(r"\b(nq_[a-z0-9_]+)\s*\(", hdr)))
+    shim = open(os.path.join(ROOT, "julia", "NQCuda.jl")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    bound = set(re.findall(r"ccall\(\(:(nq_[a-z0-9_]+), lib\)", shim))
+    assert [s for s in declared if s not in bound] == []
+    assert [s for s in bound if s not in declared] == [], "the shim binds a symbol the header does not declare"
+    assert [s for s in declared if s not in doc] == []
+
+
 def test_no_cpu_fallback(nq):
     """Without a CUDA device the product refuses to run instead of falling back."""
     import torch
