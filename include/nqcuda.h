@@ -117,7 +117,8 @@ int nq_machine_out_dtype(nq_machine_t m, nq_dtype* out);   /* ref: out_type(net)
 int nq_machine_set_params(nq_machine_t m, const void* params, int64_t P);
 int nq_machine_get_params(nq_machine_t m, void* params, int64_t P);
 
-/* logpsi!(out, net, cache, sigma[, sigma'])  -- `scol` must be NULL for RBM. out: [B] of out_type */
+/* logpsi!(out, net, cache, sigma[, sigma'])  -- `scol` must be NULL for RBM. out: [B] of out_type.
+ * ref: base_batched_networks.jl:35-40, RBMBatched.jl:37-56, RBMSplitBatched.jl:35-62, NDMBatched.jl:94-175 */
 int nq_logpsi(nq_machine_t m, const void* srow, const void* scol, nq_dtype sdtype, int64_t B, void* out);
 /* log_prob_psi!: 2*Re(log psi).  ref: base_batched_networks.jl:255-259.  out: [B] real */
 int nq_log_prob(nq_machine_t m, const void* srow, const void* scol, nq_dtype sdtype, int64_t B, void* out);
